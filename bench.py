@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py -- MLUPS / HBM-roofline benchmark of the fused collide-stream path (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (N = 1): BASELINE.json configs[1] -- D2Q9 TRT Taylor-Green vortex decay, 4096 x 4096
+periodic, Float64 (TGV(D2Q9(), 0.8, 256); CollisionModel(TRT, ...): tau_s = 0.8, Lambda = 1/4).
+N > 1: y-slab weak scaling, one 4096 x 4096 slab per GPU (global NY = 4096 N), halos exchanged
+inside liblbm_b200.so with NCCL send/recv on a side stream.
+
+One bench "step" = one device batch of `--inner` (default 100) lattice time steps: 100 is the
+reference's host-visible cadence (`next!` checks its stop criterion every 100 steps,
+src/processing_methods/track_hydrodynamic_errors.jl:55).
+  value : MLUPS with populations resident in HBM (K batches, CUDA events on the library's stream,
+          max over ranks).
+  e2e   : the same through the C ABI with HOST buffers: every bench step uploads f from pinned host
+          memory (lbm_upload_f), runs the batch (lbm_step) and downloads f (lbm_download_f).
+  roofline : achieved = B_alg * nodes / mean kernel time; B_alg = 2 Q sizeof(T) = 144 B per
+          lattice update for D2Q9 Float64; peak = MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline : the C restatement of the reference algorithm (oracle/lbm_oracle.c, OpenMP over rows,
+          all host cores) on a bounded 1024 x 1024 crop of the same workload.
+`--impl reference` times that CPU restatement alone (the reference is Julia-only and cannot run
+in this image).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "latticeboltzmann.jl_b200"))
+
+METRIC = "MLUPS (D2Q9 TRT collide-stream, million lattice updates per second)"
+Q, BYTES = 9, {"f64": 8, "f32": 4}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--inner", type=int, default=100, help="lattice time steps per bench step")
+    ap.add_argument("--nx", type=int, default=4096)
+    ap.add_argument("--ny", type=int, default=4096, help="rows PER GPU")
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--arith", default=os.environ.get("LBM_BENCH_ARITH", "exact"), choices=["exact", "fast"])
+    ap.add_argument("--lattice", default="D2Q9")
+    ap.add_argument("--collision", default="TRT", choices=["SRT", "TRT", "MRT"])
+    ap.add_argument("--variant", type=int, default=int(os.environ.get("LBM_BENCH_VARIANT", "0")))
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-n", type=int, default=1024)
+    ap.add_argument("--cpu-steps", type=int, default=100)
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU side: the oracle's C restatement (bench.py may execute oracle/ only here)
+# ---------------------------------------------------------------------------------------------
+def cpu_restatement_mlups(n, steps, lattice="D2Q9", collision="TRT", repeats=1):
+    import oracle.lbm_oracle as O
+    from oracle.c_oracle import COracle, num_threads
+    q = O.L.BY_NAME[lattice]()
+    pr = O.TGV(q, 0.8, max(n // 16, 1), NX=n, NY=n)
+    cm = O.collision_model(collision, q, pr)
+    f0 = O.initialize("ZeroVelocityInitialCondition", q, pr)
+    X, Y = pr.grid()
+    ux, uy = pr.velocity(X, Y)
+    f0 = np.stack(O.equilibrium_collision(q, pr.density(q, X, Y), ux, uy))
+    co = COracle(q, cm)
+    co.steps(f0, 2)  # warm the pages
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        co.steps(f0, steps)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return n * n * steps / best / 1e6, num_threads(), best
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    n, inner = a.cpu_n, max(1, a.cpu_steps // 10)
+    vals = []
+    threads = 1
+    for _ in range(a.warmup):
+        cpu_restatement_mlups(n, 1, a.lattice, a.collision)
+    t_all = time.perf_counter()
+    for _ in range(a.steps):
+        v, threads, _ = cpu_restatement_mlups(n, inner, a.lattice, a.collision)
+        vals.append(v)
+    wall = time.perf_counter() - t_all
+    value = float(np.mean(vals))
+    sample = f"{n}x{n} crop of the {a.nx}x{a.ny} workload, {inner} lattice steps per bench step, Float64"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "MLUPS", "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * wall / max(a.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{a.lattice} {a.collision} Taylor-Green vortex decay, periodic (BASELINE configs[1])",
+                   "grid": [n, n], "note": "Julia is not installed; CPU arm = C restatement of the reference algorithm "
+                                           "(oracle/lbm_oracle.c, -O2 -ffp-contract=off, OpenMP over rows)"},
+        "cpu_baseline": {"value": value, "unit": "MLUPS", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+def ncu_traffic(a):
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        t = json.load(open(p))
+        key = f"{a.lattice}_{a.collision}_{a.dtype}_{a.arith}_{a.nx}x{a.ny}"
+        return t.get(key)
+    return None
+
+
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    import lbm
+    from lbm import _abi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    comm = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        comm = lbm.SlabComm()
+    nx, nyl, inner = a.nx, a.ny, a.inner
+    ny = nyl * world
+    q = {"D2Q4": lbm.D2Q4, "D2Q5": lbm.D2Q5, "D2Q9": lbm.D2Q9, "D2Q13": lbm.D2Q13, "D2Q17": lbm.D2Q17,
+         "D2Q21": lbm.D2Q21, "D2Q37": lbm.D2Q37}[a.lattice]()
+    problem = lbm.TGV(q, 0.8, max(nx // 16, 1), nx, ny)
+    cm = lbm.CollisionModel({"SRT": lbm.SRT, "TRT": lbm.TRT, "MRT": lbm.MRT}[a.collision], q, problem)
+    ctx = lbm.model.make_context(q, cm, [], nx, ny, a.dtype, a.arith, comm, local)
+    ctx.set_option("variant", a.variant)
+    assert ctx.ny_local == nyl
+    # synthetic input: analytic Taylor-Green equilibrium of this rank's slab, in pinned host memory
+    pinned = torch.empty(nx * nyl * q.Q, dtype=torch.float64, pin_memory=True)
+    host = pinned.numpy().reshape((nx, nyl, q.Q), order="F")
+    host[...] = lbm.initialize(lbm.AnalyticalEquilibrium(), q, problem, rows=(ctx.y0, nyl))
+    ctx.upload_f(host)
+    ctx.set_force_none()
+
+    def barrier():
+        ctx.sync()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    t = 0
+    for _ in range(max(a.warmup, 3)):
+        ctx.step(t, inner, 1.0)
+        t += inner
+    barrier()
+    launches0 = ctx.kernel_launches
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # EXACTLY K timed bench steps, CUDA events on the library's stream, barrier + sync on both sides
+    wall0 = time.perf_counter()
+    ctx.timer_start()
+    for _ in range(a.steps):
+        ctx.step(t, inner, 1.0)
+        t += inner
+    dev_ms = ctx.timer_stop()
+    barrier()
+    region_wall = time.perf_counter() - wall0
+    launches = ctx.kernel_launches - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    region_ms = region_wall * 1e3
+    if world > 1:
+        tt = torch.tensor([dev_ms, region_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dev_ms, region_ms = [float(v) for v in tt.cpu()]
+    updates = nx * ny * inner * a.steps
+    value = updates / (dev_ms * 1e-3) / 1e6
+    b_alg = 2 * q.Q * BYTES[a.dtype]
+    kern_ms = dev_ms / (a.steps * inner)  # one fused kernel per lattice step (world == 1)
+    peak, peak_src = measured_peak()
+    achieved = b_alg * nx * nyl / (kern_ms * 1e-3) / 1e9
+    traffic = ncu_traffic(a)
+
+    # ---- e2e: host buffers in and out through the C ABI --------------------------------------
+    e2e = None
+    if not a.no_e2e:
+        out_pinned = torch.empty(nx * nyl * q.Q, dtype=torch.float64, pin_memory=True)
+        out_host = out_pinned.numpy().reshape((nx, nyl, q.Q), order="F")
+        n_e2e = max(2, min(a.steps, 5))
+        ctx.upload_f(host); ctx.step(0, inner, 1.0); ctx.download_f(out_host)  # warm
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(n_e2e):
+            ctx.upload_f(host)
+            ctx.step(0, inner, 1.0)
+            ctx.download_f(out_host)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e_s = float(tt.cpu()[0])
+        nbytes = nx * nyl * q.Q * 8
+        e2e = {"value": nx * ny * inner * n_e2e / e2e_s / 1e6, "unit": "MLUPS", "h2d_bytes_per_step": nbytes,
+               "d2h_bytes_per_step": nbytes, "bench_steps": n_e2e,
+               "note": "per bench step: lbm_upload_f(pinned host f) + lbm_step(inner) + lbm_download_f(host f)"}
+        assert np.isfinite(out_host).all()
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu:
+        v, threads, secs = cpu_restatement_mlups(a.cpu_n, a.cpu_steps, a.lattice, a.collision)
+        cpu = {"value": v, "unit": "MLUPS", "cores": threads, "kind": "port",
+               "sample": f"{a.cpu_n}x{a.cpu_n} crop, {a.cpu_steps} lattice steps ({secs:.1f} s), C restatement "
+                         f"(oracle/lbm_oracle.c) with OpenMP over rows"}
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": "MLUPS", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": a.dtype, "data": "synthetic",
+            "config": {"workload": f"{a.lattice} {a.collision} Taylor-Green vortex decay, periodic (BASELINE configs[1])",
+                       "grid_per_gpu": [nx, nyl], "grid_global": [nx, ny], "lattice_steps_per_bench_step": inner,
+                       "arith": a.arith, "variant": a.variant, "parallelism": f"y-slabs x{world}",
+                       "l2": "working set (2 x %.2f GB per GPU) >> 126 MB L2; no flush needed" % (nx * nyl * q.Q * BYTES[a.dtype] / 1e9),
+                       "wall_ms_per_step": region_ms / a.steps},
+            "clocks": clocks,
+            "e2e": e2e,
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "bytes_per_update": b_alg,
+                         "kernel_ms": kern_ms, "kernel": "k_step<%s, %s, pull>" % (a.collision, a.dtype)},
+            "cpu_baseline": cpu,
+        }))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return run_reference(a)
+    return run_b200(a)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,177 @@
+/* lbm_b200.h -- C ABI of liblbm_b200.so: the B200 (sm_100a) collide-stream-BC path of
+ * LatticeBoltzmann.jl, to be bound from Julia with `ccall`.
+ *
+ * The reference (a pure-Julia package) has no FFI seam; its seam is multiple dispatch on
+ * four generic functions called from `simulate(model, time)`
+ * (src/lattice_boltzmann_model.jl:60-77).  Each entry point below names the reference
+ * function(s) it replaces.  All citations are relative to /root/reference.
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 on success or a negative lbm_status;
+ *     the message of the last error on the calling thread is lbm_last_error().
+ *   - host population arrays use the reference's memory order: Julia `f[x, y, i]`
+ *     column-major == C `f[i][y][x]`, Float64 (src/initial_conditions.jl:13).
+ *   - x, y ranges in boundary conditions are 1-based inclusive, as `bc.xs`, `bc.ys`.
+ *   - one host thread per lbm_ctx at a time; contexts are independent.
+ *   - the library owns all device memory, streams and the NCCL communicator; host
+ *     buffers are only touched during the call that receives them.
+ *   - y-slab decomposition: with world > 1, rank r owns global rows
+ *     [lbm_local_rows().y0, +ny_local) and all host arrays passed to that context are the
+ *     local slab `[i][ny_local][nx]`.
+ */
+#ifndef LBM_B200_H
+#define LBM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LBM_ABI_VERSION 1
+#define LBM_MAX_Q 37
+#define LBM_MAX_TAU 16
+#define LBM_MAX_BCS 8
+#define LBM_NCCL_ID_BYTES 128
+
+typedef enum {
+    LBM_OK = 0,
+    LBM_ERR_INVALID = -1,     /* bad argument / descriptor */
+    LBM_ERR_UNSUPPORTED = -2, /* e.g. MovingWall in a direction the reference has no method for */
+    LBM_ERR_CUDA = -3,
+    LBM_ERR_NCCL = -4,
+    LBM_ERR_STATE = -5,       /* call not valid in the current state (e.g. stream before collide) */
+    LBM_ERR_NOMEM = -6
+} lbm_status;
+
+/* src/quadratures.jl:30-38 */
+typedef enum { LBM_D2Q4 = 0, LBM_D2Q5, LBM_D2Q9, LBM_D2Q13, LBM_D2Q17, LBM_D2Q21, LBM_D2Q37, LBM_NUM_LATTICES } lbm_lattice;
+typedef enum { LBM_F64 = 0, LBM_F32 = 1 } lbm_dtype;
+/* src/collision_models/{srt,trt,mrt}.jl */
+typedef enum { LBM_SRT = 0, LBM_TRT = 1, LBM_MRT = 2 } lbm_collision;
+/* 0: reference operation order, no FMA contraction (bit-comparable with the oracle in Float64)
+ * 1: FMA contraction + algebraic simplification allowed */
+typedef enum { LBM_ARITH_EXACT = 0, LBM_ARITH_FAST = 1 } lbm_arith;
+typedef enum { LBM_BC_BOUNCE_BACK = 0, LBM_BC_MOVING_WALL = 1 } lbm_bc_kind;
+typedef enum { LBM_NORTH = 0, LBM_EAST = 1, LBM_SOUTH = 2, LBM_WEST = 3 } lbm_direction;
+
+/* BounceBack(direction, xs, ys)            src/boundary_conditions/bounce_back.jl:2-6
+ * MovingWall(direction, xs, ys, u, rho, T) src/boundary_conditions/moving_wall.jl:5-15
+ * (MovingWall ignores xs/ys and only exists for North, moving_wall.jl:17-38.) */
+typedef struct {
+    int32_t kind;      /* lbm_bc_kind */
+    int32_t direction; /* lbm_direction */
+    int32_t x0, x1, y0, y1;
+    double u[2];
+    double rho;
+    double T;
+} lbm_bc;
+
+/* Everything `LatticeBoltzmannModel(problem, q; collision_model, ...)` fixes
+ * (src/lattice_boltzmann_model.jl:15-33). */
+typedef struct {
+    int32_t abi_version; /* LBM_ABI_VERSION */
+    int32_t nx, ny;      /* GLOBAL grid size (problem.NX, problem.NY) */
+    int32_t lattice;     /* lbm_lattice */
+    int32_t dtype;       /* lbm_dtype: storage + arithmetic type on the device */
+    int32_t collision;   /* lbm_collision */
+    int32_t arith;       /* lbm_arith */
+    int32_t ntau;
+    /* SRT: tau[0]=tau (srt.jl:2).  TRT: tau[0]=tau_symmetric, tau[1]=tau_asymmetric (trt.jl:2-3).
+     * MRT: tau[n-1] relaxes the n-th Hermite coefficient, ntau >= 2 when a force is set (mrt.jl:94,104). */
+    double tau[LBM_MAX_TAU];
+    int32_t n_bcs;
+    lbm_bc bcs[LBM_MAX_BCS]; /* applied in this order after streaming (boundary_conditions.jl:13-15) */
+    int32_t device;          /* CUDA device ordinal */
+    int32_t rank, world;     /* y-slab decomposition; world == 1: single GPU */
+    uint8_t nccl_id[LBM_NCCL_ID_BYTES]; /* from lbm_nccl_unique_id() on rank 0, same on all ranks */
+} lbm_desc;
+
+typedef struct lbm_ctx lbm_ctx;
+
+int lbm_abi_version(void);
+const char *lbm_last_error(void);
+
+/* Built-in constant tables of a quadrature, for the host to check its own against:
+ * q.abscissae / q.weights / q.speed_of_sound_squared (src/quadratures/D2Q*.jl), opposite(q, i)
+ * (0-based here; src/quadratures.jl:11-19 and per-lattice overrides), the truncation order of
+ * the collision equilibrium (velocity_distribution_function/quadratures.jl) and div(order(q), 2).
+ * Arrays must hold LBM_MAX_Q entries; any pointer may be NULL. */
+int lbm_lattice_info(int32_t lattice, int32_t *q, int32_t *cx, int32_t *cy, double *w, double *css,
+                     int32_t *opposite, int32_t *eq_order, int32_t *hermite_order, int32_t *halo);
+
+/* Rank 0 creates the id; the host broadcasts the bytes to the other ranks (any transport). */
+int lbm_nccl_unique_id(uint8_t id[LBM_NCCL_ID_BYTES]);
+
+int lbm_create(const lbm_desc *desc, lbm_ctx **out);
+void lbm_destroy(lbm_ctx *ctx);
+int lbm_local_rows(const lbm_ctx *ctx, int32_t *y0, int32_t *ny_local);
+
+/* model.f_stream = f / copy(model.f_stream) / copy(model.f_collision)
+ * (lattice_boltzmann_model.jl:8-9).  Host Float64 arrays [q][ny_local][nx]. */
+int lbm_upload_f(lbm_ctx *ctx, const double *f);
+/* model.f_collision = f: for callers that hand stream!/apply! their own post-collision array
+ * (stream!(q, f, f_new), apply!(bcs, q, f_new, f_old)); call after lbm_upload_f. */
+int lbm_upload_f_collision(lbm_ctx *ctx, const double *f);
+int lbm_download_f(lbm_ctx *ctx, double *f);
+int lbm_download_f_collision(lbm_ctx *ctx, double *f);
+
+/* The force closure `collision_model.force(x_idx, y_idx, time)` (srt.jl:10-12,52; trt.jl:17-18,77;
+ * mrt.jl:40-41,92) as data, already in lattice units (lattice_force, problems/problems.jl:103-104). */
+int lbm_set_force_none(lbm_ctx *ctx);
+int lbm_set_force_uniform(lbm_ctx *ctx, double fx, double fy);
+/* static per-node field F[2][ny_local][nx] */
+int lbm_set_force_field(lbm_ctx *ctx, const double *F);
+/* time-dependent separable force for steps t0 .. t0+nsteps-1:
+ * F_x(x, y, t) = fx_of_y[t - t0][y],  F_y(x, y, t) = fy_of_x[t - t0][x]
+ * (DecayingShearFlow, problems/decaying_shear_flow.jl:131-147). */
+int lbm_set_force_separable(lbm_ctx *ctx, int64_t t0, int32_t nsteps, const double *fx_of_y, const double *fy_of_x);
+
+/* collide!(model; time): f_stream -> f_collision   (lattice_boltzmann_model.jl:84-92;
+ * srt.jl:18-62, trt.jl:42-97, mrt.jl:56-118).  `step` selects the row of a separable force table. */
+int lbm_collide(lbm_ctx *ctx, int64_t step, double time);
+/* stream!(model): f_collision -> f_stream, fully periodic pull (lattice_boltzmann_model.jl:94-96; stream.jl:19-30) */
+int lbm_stream(lbm_ctx *ctx);
+/* apply_boundary_conditions!(model; time)  (lattice_boltzmann_model.jl:98-106; bounce_back.jl, moving_wall.jl) */
+int lbm_apply_bcs(lbm_ctx *ctx, double time);
+/* The body of `for t in time` (lattice_boltzmann_model.jl:64-67), nsteps times, fused on the
+ * device: for t = t0 .. t0+nsteps-1: collide(time = t*dt) -> stream -> apply BCs. Asynchronous. */
+int lbm_step(lbm_ctx *ctx, int64_t t0, int64_t nsteps, double dt);
+int lbm_sync(lbm_ctx *ctx);
+
+/* Per-node hydrodynamic fields of f_stream, host Float64 arrays [ny_local][nx], NULL = skip:
+ *   rho, ux, uy : density / velocity! (moments.jl:3-19), lattice units
+ *   p           : pressure(q, f, rho, u) (moments.jl:21-33; 1.0 for D2Q4/D2Q5)
+ *   p_track, sxx, sxy, syy : the TrackHydrodynamicErrors pressure tr(P)/D and
+ *                 deviatoric_tensor(q, tau_visc, f, rho, u) (track_hydrodynamic_errors.jl:150-181,
+ *                 moments.jl:81-96), tau_visc = css * lattice_viscosity(problem). */
+int lbm_moments(lbm_ctx *ctx, double tau_visc, double *rho, double *ux, double *uy, double *p,
+                double *p_track, double *sxx, double *sxy, double *syy);
+
+typedef enum {
+    /* out[0] = sum of lattice u_x over local nodes, out[1] = node count, out[2] = #NaN nodes
+     * (MeanVelocityStoppingCriteria, stopping_criteria.jl:17-55) */
+    LBM_REDUCE_MEAN_UX = 0,
+    /* out[0] = sum |u - u_old|^2, out[1] = sum |u_old|^2, then u_old := u
+     * (VelocityConvergenceStoppingCriteria, stopping_criteria.jl:71-115) */
+    LBM_REDUCE_VELOCITY_CHANGE = 1,
+    /* out[0] = sum rho, out[1] = sum rho*(ux+uy), out[2] = sum rho*(ux^2+uy^2) in lattice units
+     * (track_hydrodynamic_errors.jl:200-202 before unit scaling) */
+    LBM_REDUCE_CONSERVED = 2
+} lbm_reduce_kind;
+/* Local (per-rank) partial sums; the host adds ranks. */
+int lbm_reduce(lbm_ctx *ctx, int32_t kind, double *out, int32_t n);
+
+/* Introspection used by bench.py / tests. */
+int64_t lbm_kernel_launches(const lbm_ctx *ctx); /* kernels launched by this context so far */
+int lbm_last_step_ms(lbm_ctx *ctx, float *ms);    /* CUDA-event time of the last lbm_step batch */
+/* CUDA events on the library's own stream (torch.cuda.Event cannot see it): start, ...work..., stop
+ * (synchronises and returns the elapsed device time). */
+int lbm_timer_start(lbm_ctx *ctx);
+int lbm_timer_stop(lbm_ctx *ctx, float *ms);
+int lbm_set_option(lbm_ctx *ctx, const char *key, int64_t value); /* tuning knobs, see DESIGN.md */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LBM_B200_H */

@@ -1,0 +1,91 @@
+// Types shared by the context code (lbm_b200.cu) and the per-lattice kernel translation units
+// (kernels_inst.cu compiled once per <lattice, arithmetic mode>).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "lattices.h"
+
+namespace lbm {
+
+// Device layout of one population buffer (all planes identical):
+//   element (i, y, x), y in [-GY, nyl+GY), x in [-GX, nx+GX)  ->  base[i*plane + y*pitch + x]
+// where `base` already points at (0, 0, 0).  Ghost cells hold periodic images (x always; y when
+// world == 1) or the neighbouring slab's rows (world > 1), so the pull never wraps.
+
+struct BCd {  // device view of one boundary condition (global, 1-based inclusive ranges)
+    int kind, dir;
+    int x0, x1, y0, y1;
+    double ax, ay;  // MovingWall: equilibrium_coefficient(Val{1}) = rho_w * u_w (moving_wall.jl:20)
+};
+
+template <typename T>
+struct KParams {
+    const T *src;  // pulled / read buffer
+    T *dst;        // written buffer
+    const T *aux;  // f_old (post-collision) for the standalone BC kernel
+    long long pitch, plane;
+    int nx, nyl;   // local interior size
+    int y0g, nyg;  // first global row of this slab, global row count
+    int row_a0, row_an, row_b0, nrows;  // launched rows r -> local row (r < row_an ? row_a0 + r : row_b0 + r - row_an)
+    int wrap_y;    // 1: this slab is the whole periodic domain in y -> kernels write the y images too
+    // collision constants (already converted to T):
+    //   SRT: c[0] = 1 - 1/tau, c[1] = 1/tau, shift = tau
+    //   TRT: c[0] = -(1/tau_s), c[1] = 1/tau_a, shift = tau_a
+    //   MRT: c[2n] = 1 - 1/tau_n, c[2n+1] = 1/tau_n (n = 2..4), k[n] = css^n / n!, shift = tau_2
+    T c[12];
+    T kn[5];
+    T shift;
+    int mrt_skip[5];  // tau_n == 1 -> a_coll[n] = a_eq[n] exactly; skip the projection of f
+    // forcing
+    int force_mode;  // 0 none, 1 uniform, 2 field, 3 separable table
+    T fx, fy;
+    const T *field;   // [2][nyl][nx]
+    const T *sep_fx;  // [nsteps][nyl]
+    const T *sep_fy;  // [nsteps][nx]
+    long long sep_t0;
+    // boundary conditions
+    int nbc;
+    BCd bc[LBM_MAX_BCS];
+};
+
+struct MomentsOut {  // device Float64 arrays [nyl][nx] or nullptr
+    double *rho, *ux, *uy, *p, *p_track, *sxx, *sxy, *syy;
+    double tau_visc;
+};
+
+struct ReduceArgs {
+    int kind;
+    double *partials;  // [nblocks][4]
+    double *u_old;     // [2][nyl][nx] for LBM_REDUCE_VELOCITY_CHANGE
+    double *out;       // [4] device
+    int nblocks;
+};
+
+// Launchers exported by one kernels_inst.cu instance.
+struct Ops {
+    int lattice, arith;
+    // collide (+ optional fused pull of the previous step's stream + BCs)
+    void (*step64)(int cm, bool pull, const KParams<double> &p, long long step, int variant, cudaStream_t s);
+    void (*step32)(int cm, bool pull, const KParams<float> &p, long long step, int variant, cudaStream_t s);
+    // periodic pull (+ BCs when p.nbc > 0) without collision
+    void (*stream64)(const KParams<double> &p, cudaStream_t s);
+    void (*stream32)(const KParams<float> &p, cudaStream_t s);
+    // standalone apply!(bcs, q, f_new = dst, f_old = aux)
+    void (*bcs64)(const KParams<double> &p, cudaStream_t s);
+    void (*bcs32)(const KParams<float> &p, cudaStream_t s);
+    // ghost refresh of `dst` (periodic images)
+    void (*ghosts64)(const KParams<double> &p, cudaStream_t s);
+    void (*ghosts32)(const KParams<float> &p, cudaStream_t s);
+    void (*moments64)(bool pull, const KParams<double> &p, const MomentsOut &m, cudaStream_t s);
+    void (*moments32)(bool pull, const KParams<float> &p, const MomentsOut &m, cudaStream_t s);
+    void (*reduce64)(bool pull, const KParams<double> &p, const ReduceArgs &r, cudaStream_t s);
+    void (*reduce32)(bool pull, const KParams<float> &p, const ReduceArgs &r, cudaStream_t s);
+    // host f64 [q][nyl][nx] staging <-> device storage conversion (f32 stores f - w)
+    void (*import32)(const KParams<float> &p, const double *staging, int plane_idx, cudaStream_t s);
+    void (*export32)(const KParams<float> &p, double *staging, int plane_idx, cudaStream_t s);
+    int (*init_constants)();  // uploads the __constant__ lattice tables on the current device
+};
+
+const Ops *get_ops(int lattice, int arith);
+
+}  // namespace lbm

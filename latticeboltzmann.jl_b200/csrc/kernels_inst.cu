@@ -1,0 +1,675 @@
+// Hand-written sm_100a kernels of the collide -> stream -> boundary-condition path, compiled once
+// per <LBM_LATTICE, LBM_FAST>:
+//   LBM_FAST=0  ("exact"): built with -fmad=false; every expression keeps the operation order of
+//               the reference (and of oracle/), so Float64 SRT/TRT results are bit-identical to
+//               the oracle.
+//   LBM_FAST=1  ("fast"):  same source, FMA contraction on.
+// Reference lines restated here (under /root/reference/src):
+//   density/velocity!  velocity_distribution_function/moments.jl:3-19
+//   equilibrium!       velocity_distribution_function/maxwell_boltzmann_equilibrium.jl:12-66,
+//                      velocity_distribution_function/quadratures.jl:3-159
+//   collide!           collision_models/srt.jl:18-62, trt.jl:42-97, mrt.jl:56-118
+//   stream!            stream.jl:19-30,69-74
+//   apply!             boundary_conditions/bounce_back.jl:8-72, moving_wall.jl:17-38
+//   diagnostics        moments.jl:21-96, processing_methods/track_hydrodynamic_errors.jl:134-186,
+//                      processing_methods/stopping_criteria/stopping_criteria.jl:17-115
+#include <type_traits>
+#include <utility>
+#include "common.h"
+
+#ifndef LBM_LATTICE
+#error "compile with -DLBM_LATTICE=<lbm_lattice value> -DLBM_FAST=<0|1>"
+#endif
+#ifndef LBM_FAST
+#define LBM_FAST 0
+#endif
+#define LBM_CAT2(a, b, c) a##b##_##c
+#define LBM_CAT(a, b, c) LBM_CAT2(a, b, c)
+#define LBM_NS LBM_CAT(inst_, LBM_LATTICE, LBM_FAST)
+
+namespace lbm {
+namespace LBM_NS {
+
+using L = Lat<LBM_LATTICE>;
+constexpr int Q = L::Q;
+constexpr int H = L::H;
+constexpr int NH = L::N;
+
+// ------------------------------------------------------------------------------------------
+// lattice constants in constant memory (operands of DFMA/FFMA come straight from the bank)
+// ------------------------------------------------------------------------------------------
+template <typename T>
+struct LatConst {
+    T w[Q];
+    T css, cs_inv;
+    T H2[Q][3];  // hermite(Val{2}, c_i, q): xx, xy, yy          (hermite_polynomials.jl:47-51)
+    T H3[Q][4];  // xxx, xxy, xyy, yyy                            (:52-61)
+    T H4[Q][5];  // xxxx, xxxy, xxyy, xyyy, yyyy                  (:63-82)
+};
+__constant__ LatConst<double> c_lat64;
+__constant__ LatConst<float> c_lat32;
+
+template <typename T> __device__ __forceinline__ const LatConst<T> &LC();
+template <> __device__ __forceinline__ const LatConst<double> &LC<double>() { return c_lat64; }
+template <> __device__ __forceinline__ const LatConst<float> &LC<float>() { return c_lat32; }
+
+static double hermite_entry(int n, const int *idx, const int *xi, double cs) {
+    auto d = [](int a, int b) { return a == b ? 1 : 0; };
+    if (n == 2) { int a = idx[0], b = idx[1]; return (double)(xi[b] * xi[a]) - cs * d(a, b); }
+    if (n == 3) {
+        int a = idx[0], b = idx[1], c = idx[2];
+        return (double)(xi[c] * xi[b] * xi[a]) - cs * (double)(xi[a] * d(b, c) + xi[b] * d(a, c) + xi[c] * d(a, b));
+    }
+    int a = idx[0], b = idx[1], c = idx[2], e = idx[3];
+    return (double)(xi[e] * xi[c] * xi[b] * xi[a])
+           - cs * (double)(xi[a] * xi[b] * d(c, e) + xi[a] * xi[c] * d(b, e) + xi[a] * xi[e] * d(b, c)
+                           + xi[b] * xi[c] * d(a, e) + xi[b] * xi[e] * d(a, c) + xi[c] * xi[e] * d(a, b))
+           + (cs * cs) * (double)(d(a, b) * d(c, e) + d(a, c) * d(b, e) + d(a, e) * d(b, c));
+}
+
+static int init_constants() {
+    LatticeInfo li;
+    lattice_info(LBM_LATTICE, li);
+    LatConst<double> h;
+    LatConst<float> hf;
+    h.css = li.css;
+    h.cs_inv = 1 / li.css;
+    for (int i = 0; i < Q; ++i) {
+        h.w[i] = li.w[i];
+        const int xi[2] = {li.cx[i], li.cy[i]};
+        for (int k = 0; k <= 2; ++k) { int idx[2] = {0, 0}; for (int j = 0; j < k; ++j) idx[1 - j] = 1; h.H2[i][k] = hermite_entry(2, idx, xi, h.cs_inv); }
+        for (int k = 0; k <= 3; ++k) { int idx[3] = {0, 0, 0}; for (int j = 0; j < k; ++j) idx[2 - j] = 1; h.H3[i][k] = hermite_entry(3, idx, xi, h.cs_inv); }
+        for (int k = 0; k <= 4; ++k) { int idx[4] = {0, 0, 0, 0}; for (int j = 0; j < k; ++j) idx[3 - j] = 1; h.H4[i][k] = hermite_entry(4, idx, xi, h.cs_inv); }
+    }
+    hf.css = (float)h.css; hf.cs_inv = (float)h.cs_inv;
+    for (int i = 0; i < Q; ++i) {
+        hf.w[i] = (float)h.w[i];
+        for (int k = 0; k < 3; ++k) hf.H2[i][k] = (float)h.H2[i][k];
+        for (int k = 0; k < 4; ++k) hf.H3[i][k] = (float)h.H3[i][k];
+        for (int k = 0; k < 5; ++k) hf.H4[i][k] = (float)h.H4[i][k];
+    }
+    if (cudaMemcpyToSymbol(c_lat64, &h, sizeof(h)) != cudaSuccess) return -1;
+    if (cudaMemcpyToSymbol(c_lat32, &hf, sizeof(hf)) != cudaSuccess) return -1;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// compile-time loops over populations
+// ------------------------------------------------------------------------------------------
+template <int B, int E, class F>
+__device__ __forceinline__ void static_for(F &&f) {
+    if constexpr (B < E) {
+        f(std::integral_constant<int, B>{});
+        static_for<B + 1, E>(f);
+    }
+}
+
+// c * u for a compile-time integer c, with the trivial cases folded (value-identical to the
+// reference's Float64(c) * u up to the sign of zero).
+template <int C, typename T>
+__device__ __forceinline__ T cmul(T u) {
+    if constexpr (C == 0) return T(0);
+    else if constexpr (C == 1) return u;
+    else if constexpr (C == -1) return -u;
+    else return T(C) * u;
+}
+template <int CX, int CY, typename T>
+__device__ __forceinline__ T cdot(T ux, T uy) {  // abscissae[1,i]*u[1] + abscissae[2,i]*u[2]
+    if constexpr (CX == 0 && CY == 0) return T(0);
+    else if constexpr (CY == 0) return cmul<CX>(ux);
+    else if constexpr (CX == 0) return cmul<CY>(uy);
+    else return cmul<CX>(ux) + cmul<CY>(uy);
+}
+
+// ------------------------------------------------------------------------------------------
+// boundary-condition resolution for the fused pull
+// ------------------------------------------------------------------------------------------
+// Which boundary condition (last in list order wins, boundary_conditions.jl:13-15) overwrites
+// population i at the 1-based global node (x1, y1)?  (cxo, cyo) = c[opposite(i)].  -1: none.
+template <typename T>
+__device__ __noinline__ int resolve_bc(const KParams<T> &p, int x1, int y1, int cxo, int cyo) {
+    for (int b = p.nbc - 1; b >= 0; --b) {
+        const BCd &bc = p.bc[b];
+        bool hit;
+        switch (bc.dir) {
+        case LBM_NORTH: hit = (y1 + cyo > p.nyg); break;  // bounce_back.jl:15, moving_wall.jl:29
+        case LBM_SOUTH: hit = (y1 + cyo <= 0); break;     // bounce_back.jl:31
+        case LBM_EAST: hit = (x1 + cxo > p.nx); break;    // bounce_back.jl:48
+        default: hit = (x1 + cxo <= 0); break;            // bounce_back.jl:64
+        }
+        if (!hit) continue;
+        if (bc.kind == LBM_BC_MOVING_WALL) return b;  // ignores xs/ys (moving_wall.jl:28,32)
+        if (x1 >= bc.x0 && x1 <= bc.x1 && y1 >= bc.y0 && y1 <= bc.y1) return b;
+    }
+    return -1;
+}
+
+template <typename T>
+__device__ __forceinline__ bool near_wall(const KParams<T> &p, int x, int yg) {
+    return p.nbc > 0 && (x < H || x >= p.nx - H || yg < H || yg >= p.nyg - H);
+}
+
+// f_new[x,y,i] = f_old[x,y,opp(i)] (+ 2 a_1 for a moving wall), a_1 = w_i * css * dot(rho_w u_w, c_i)
+template <int I, typename T>
+__device__ __forceinline__ T bounced(const KParams<T> &p, int b, T f_opp) {
+    if (p.bc[b].kind == LBM_BC_MOVING_WALL) {
+        const LatConst<T> &c = LC<T>();
+        const T ax = T(p.bc[b].ax), ay = T(p.bc[b].ay);
+        const T a1 = (c.w[I] * c.css) * (ax * T(L::cx(I)) + ay * T(L::cy(I)));
+        return f_opp + 2 * a1;
+    }
+    return f_opp;
+}
+
+// ------------------------------------------------------------------------------------------
+// node load / store
+// ------------------------------------------------------------------------------------------
+// PULL = false: f[i] = src[i, y, x]
+// PULL = true : f[i] = (stream + BCs)(src)[i, y, x]  i.e. src[i, y - c_y, x - c_x] unless a boundary
+//               condition overwrites it with src[opp(i), y, x].
+template <typename T, bool PULL>
+__device__ __forceinline__ void load_node(const KParams<T> &p, int x, int y, T (&f)[Q]) {
+    const T *base = p.src + (long long)y * p.pitch + x;
+    static_for<0, Q>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        if constexpr (PULL) {
+            f[i] = __ldg(base + (i * p.plane - L::cy(i) * p.pitch - L::cx(i)));
+        } else {
+            f[i] = __ldg(base + i * p.plane);
+        }
+    });
+    if constexpr (PULL) {
+        const int yg = p.y0g + y;
+        if (near_wall(p, x, yg)) {
+            static_for<0, Q>([&](auto I) {
+                constexpr int i = decltype(I)::value;
+                constexpr int o = L::opp(i);
+                if constexpr (i != o) {
+                    const int b = resolve_bc(p, x + 1, yg + 1, L::cx(o), L::cy(o));
+                    if (b >= 0) f[i] = bounced<i>(p, b, __ldg(base + o * p.plane));
+                }
+            });
+        }
+    }
+}
+
+// Stores the node and, for nodes within H of the slab edge, its periodic images inside the
+// ghost frame (all planes share the offsets).  Image loops are runtime, population loops unrolled,
+// so `out` stays in registers.
+template <typename T, bool GHOSTS>
+__device__ __forceinline__ void store_node(const KParams<T> &p, int x, int y, T (&out)[Q]) {
+    T *d = p.dst + (long long)y * p.pitch + x;
+    static_for<0, Q>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        d[i * p.plane] = out[i];
+    });
+    if constexpr (GHOSTS) {
+        const bool ex = (x < H) || (x >= p.nx - H);
+        const bool ey = p.wrap_y && ((y < H) || (y >= p.nyl - H));
+        if (ex || ey) {
+            const int kx_lo = -((x + H) / p.nx), kx_hi = (p.nx + H - 1 - x) / p.nx;
+            int ky_lo = 0, ky_hi = 0;
+            if (p.wrap_y) { ky_lo = -((y + H) / p.nyl); ky_hi = (p.nyl + H - 1 - y) / p.nyl; }
+            for (int ky = ky_lo; ky <= ky_hi; ++ky)
+                for (int kx = kx_lo; kx <= kx_hi; ++kx) {
+                    if (kx == 0 && ky == 0) continue;
+                    T *g = d + (long long)(ky * p.nyl) * p.pitch + kx * p.nx;
+                    static_for<0, Q>([&](auto I) {
+                        constexpr int i = decltype(I)::value;
+                        g[i * p.plane] = out[i];
+                    });
+                }
+        }
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ int launched_row(const KParams<T> &p, int r) {
+    return r < p.row_an ? p.row_a0 + r : p.row_b0 + (r - p.row_an);
+}
+
+// ------------------------------------------------------------------------------------------
+// moments and equilibrium
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void rho_u(const T (&f)[Q], T &rho, T &ux, T &uy) {
+    // density = sum(f) (left fold, moments.jl:3); velocity! (moments.jl:5-19)
+    rho = f[0];
+    static_for<1, Q>([&](auto I) { rho = rho + f[decltype(I)::value]; });
+    T jx = T(0), jy = T(0);
+    static_for<0, Q>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        if constexpr (L::cx(i) != 0) jx = jx + cmul<L::cx(i)>(f[i]);
+    });
+    static_for<0, Q>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        if constexpr (L::cy(i) != 0) jy = jy + cmul<L::cy(i)>(f[i]);
+    });
+    ux = jx / rho;
+    uy = jy / rho;
+}
+
+template <typename T>
+__device__ __forceinline__ T pow4(T x) { const T x2 = x * x; return x2 * x2; }
+
+// _equilibrium(q, rho, w_i, u.c_i, u.u, T = 1, ...) for compile-time i.
+template <int I, typename T>
+__device__ __forceinline__ T feq_i(T rho, T ux, T uy, T u2) {
+    const LatConst<T> &c = LC<T>();
+    const T cs = c.css;
+    constexpr bool REST = (L::cx(I) == 0 && L::cy(I) == 0);
+    const T udx = cdot<L::cx(I), L::cy(I)>(ux, uy);
+    T poly;
+    if constexpr (REST) poly = T(1);
+    else poly = T(1) + cs * udx;
+    if constexpr (L::EQ_ORDER >= 2) {
+        T a2;
+        if constexpr (REST) a2 = (-cs) * u2;
+        else a2 = (cs * cs) * (udx * udx) + (-cs) * u2;
+        poly = poly + T(0.5) * a2;
+    }
+    if constexpr (L::EQ_ORDER >= 3 && !REST) {
+        const T a3 = (cs * udx) * ((cs * cs) * (udx * udx) - (3 * cs) * u2);
+        poly = poly + T(1.0 / 6) * a3;
+    }
+    if constexpr (L::EQ_ORDER >= 4) {
+        T a4;
+        if constexpr (REST) a4 = (3 * (cs * cs)) * (u2 * u2);
+        else a4 = ((pow4(cs) * pow4(udx)) - ((6 * (cs * cs * cs)) * u2) * (udx * udx)) + (3 * (cs * cs)) * (u2 * u2);
+        poly = poly + T(1.0 / 24) * a4;
+    }
+    return (rho * c.w[I]) * poly;
+}
+
+// ------------------------------------------------------------------------------------------
+// collision operators (Float64 / raw populations)
+// ------------------------------------------------------------------------------------------
+template <int CM, typename T>
+__device__ __forceinline__ void collide_node(const KParams<T> &p, const T (&f)[Q], bool forced, T Fx, T Fy, T (&out)[Q]) {
+    T rho, ux, uy;
+    rho_u(f, rho, ux, uy);
+    if (forced) {  // equilibrium velocity shift u + tau F (srt.jl:54, trt.jl:79, mrt.jl:94)
+        ux = ux + p.shift * Fx;
+        uy = uy + p.shift * Fy;
+    }
+    if constexpr (CM == LBM_SRT) {
+        const T u2 = ux * ux + uy * uy;
+        static_for<0, Q>([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            out[i] = p.c[0] * f[i] + p.c[1] * feq_i<i>(rho, ux, uy, u2);  // srt.jl:58
+        });
+    } else if constexpr (CM == LBM_TRT) {
+        const T u2 = ux * ux + uy * uy;
+        T feq[Q];
+        static_for<0, Q>([&](auto I) { feq[decltype(I)::value] = feq_i<decltype(I)::value>(rho, ux, uy, u2); });
+        static_for<0, Q>([&](auto I) {  // trt.jl:82-94
+            constexpr int i = decltype(I)::value;
+            constexpr int o = L::opp(i);
+            const T feq_s = T(0.5) * (feq[i] + feq[o]);
+            const T feq_a = T(0.5) * (feq[i] - feq[o]);
+            const T f_s = T(0.5) * (f[i] + f[o]);
+            const T f_a = T(0.5) * (f[i] - f[o]);
+            out[i] = f[i] + (p.c[0] * (f_s - feq_s) - p.c[1] * (f_a - feq_a));
+        });
+    } else {
+        // regularised MRT (mrt.jl:56-118) with the symmetric tensors reduced to their unique
+        // components: a^(n) has n+1 of them, multiplicity C(n,k).
+        const LatConst<T> &c = LC<T>();
+        T a2[3] = {T(0), T(0), T(0)}, a3[4] = {T(0), T(0), T(0), T(0)}, a4[5] = {T(0), T(0), T(0), T(0), T(0)};
+        if constexpr (NH >= 2) {
+            if (!p.mrt_skip[2]) {
+                static_for<0, Q>([&](auto I) {
+                    constexpr int i = decltype(I)::value;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) a2[k] = a2[k] + f[i] * c.H2[i][k];
+                });
+            }
+            const T e[3] = {rho * (ux * ux), rho * (ux * uy), rho * (uy * uy)};
+            const T m[3] = {T(1), T(2), T(1)};
+#pragma unroll
+            for (int k = 0; k < 3; ++k) a2[k] = (p.kn[2] * m[k]) * (p.c[4] * a2[k] + p.c[5] * e[k]);
+        }
+        if constexpr (NH >= 3) {
+            if (!p.mrt_skip[3]) {
+                static_for<0, Q>([&](auto I) {
+                    constexpr int i = decltype(I)::value;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) a3[k] = a3[k] + f[i] * c.H3[i][k];
+                });
+            }
+            const T e[4] = {rho * (ux * ux * ux), rho * (ux * ux * uy), rho * (ux * uy * uy), rho * (uy * uy * uy)};
+            const T m[4] = {T(1), T(3), T(3), T(1)};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) a3[k] = (p.kn[3] * m[k]) * (p.c[6] * a3[k] + p.c[7] * e[k]);
+        }
+        if constexpr (NH >= 4) {
+            if (!p.mrt_skip[4]) {
+                static_for<0, Q>([&](auto I) {
+                    constexpr int i = decltype(I)::value;
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) a4[k] = a4[k] + f[i] * c.H4[i][k];
+                });
+            }
+            const T x2 = ux * ux, y2 = uy * uy;
+            const T e[5] = {rho * (x2 * x2), rho * (x2 * ux * uy), rho * (x2 * y2), rho * (ux * uy * y2), rho * (y2 * y2)};
+            const T m[5] = {T(1), T(4), T(6), T(4), T(1)};
+#pragma unroll
+            for (int k = 0; k < 5; ++k) a4[k] = (p.kn[4] * m[k]) * (p.c[8] * a4[k] + p.c[9] * e[k]);
+        }
+        const T csrho = c.css * rho;
+        static_for<0, Q>([&](auto I) {  // mrt.jl:107-114
+            constexpr int i = decltype(I)::value;
+            T acc = rho + csrho * cdot<L::cx(i), L::cy(i)>(ux, uy);
+            if constexpr (NH >= 2) {
+                T hs = a2[0] * c.H2[i][0];
+                hs = hs + a2[1] * c.H2[i][1];
+                hs = hs + a2[2] * c.H2[i][2];
+                if constexpr (NH >= 3) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) hs = hs + a3[k] * c.H3[i][k];
+                }
+                if constexpr (NH >= 4) {
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) hs = hs + a4[k] * c.H4[i][k];
+                }
+                acc = acc + hs;
+            }
+            out[i] = c.w[i] * acc;
+        });
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ bool load_force(const KParams<T> &p, int x, int y, long long step, T &Fx, T &Fy) {
+    Fx = T(0); Fy = T(0);
+    switch (p.force_mode) {
+    case 0: return false;
+    case 1: Fx = p.fx; Fy = p.fy; return true;
+    case 2: {
+        const long long n = (long long)y * p.nx + x;
+        Fx = __ldg(p.field + n);
+        Fy = __ldg(p.field + (long long)p.nyl * p.nx + n);
+        return true;
+    }
+    default: {
+        const long long s = step - p.sep_t0;
+        Fx = __ldg(p.sep_fx + s * p.nyl + y);
+        Fy = __ldg(p.sep_fy + s * p.nx + x);
+        return true;
+    }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1/K2: collide, optionally fused with the pull (stream + BCs) of the previous step
+// ------------------------------------------------------------------------------------------
+template <int CM, typename T, bool PULL>
+__global__ void __launch_bounds__(256) k_step(const __grid_constant__ KParams<T> p, long long step) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= p.nx) return;
+    for (int r = blockIdx.y * blockDim.y + threadIdx.y; r < p.nrows; r += gridDim.y * blockDim.y) {
+        const int y = launched_row(p, r);
+        T f[Q], out[Q];
+        load_node<T, PULL>(p, x, y, f);
+        T Fx, Fy;
+        const bool forced = load_force(p, x, y, step, Fx, Fy);
+        collide_node<CM, T>(p, f, forced, Fx, Fy, out);
+        store_node<T, true>(p, x, y, out);
+    }
+}
+
+// K3: stream (+BC) only:  dst interior = pull(src)
+template <typename T>
+__global__ void __launch_bounds__(256) k_stream(const __grid_constant__ KParams<T> p) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= p.nx) return;
+    for (int r = blockIdx.y * blockDim.y + threadIdx.y; r < p.nrows; r += gridDim.y * blockDim.y) {
+        const int y = launched_row(p, r);
+        T f[Q];
+        load_node<T, true>(p, x, y, f);
+        store_node<T, false>(p, x, y, f);
+    }
+}
+
+// K4: standalone apply!(bcs, q, f_new = dst, f_old = aux): overwrite in place
+template <typename T>
+__global__ void __launch_bounds__(256) k_bcs(const __grid_constant__ KParams<T> p) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= p.nx) return;
+    for (int r = blockIdx.y * blockDim.y + threadIdx.y; r < p.nrows; r += gridDim.y * blockDim.y) {
+        const int y = launched_row(p, r);
+        const int yg = p.y0g + y;
+        if (!near_wall(p, x, yg)) continue;
+        const long long n = (long long)y * p.pitch + x;
+        static_for<0, Q>([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            constexpr int o = L::opp(i);
+            if constexpr (i != o) {
+                const int b = resolve_bc(p, x + 1, yg + 1, L::cx(o), L::cy(o));
+                if (b >= 0) p.dst[i * p.plane + n] = bounced<i>(p, b, p.aux[o * p.plane + n]);
+            }
+        });
+    }
+}
+
+// ghost refresh: every ghost cell of dst := its periodic source (x always, y when wrap_y)
+template <typename T>
+__global__ void __launch_bounds__(256) k_ghosts(const __grid_constant__ KParams<T> p) {
+    const int W = p.nx + 2 * H;
+    const int xx = blockIdx.x * blockDim.x + threadIdx.x - H;  // [-H, nx+H)
+    if (xx >= p.nx + H) return;
+    const int ylo = p.wrap_y ? -H : 0, yhi = p.wrap_y ? p.nyl + H : p.nyl;
+    for (int yy = ylo + blockIdx.y * blockDim.y + threadIdx.y; yy < yhi; yy += gridDim.y * blockDim.y) {
+        const bool gx = (xx < 0 || xx >= p.nx), gy = (yy < 0 || yy >= p.nyl);
+        if (!gx && !gy) continue;
+        int xs = xx % p.nx; if (xs < 0) xs += p.nx;
+        int ys = yy;
+        if (gy) { ys = yy % p.nyl; if (ys < 0) ys += p.nyl; }
+        T *d = p.dst + (long long)yy * p.pitch + xx;
+        const T *s = p.dst + (long long)ys * p.pitch + xs;
+        for (int i = 0; i < Q; ++i) d[i * p.plane] = s[i * p.plane];
+    }
+    (void)W;
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: diagnostics
+// ------------------------------------------------------------------------------------------
+template <typename T>
+struct NodeDiag { double rho, ux, uy, axx, axy, ayy; };
+
+template <typename T, bool PULL>
+__device__ __forceinline__ void node_fields(const KParams<T> &p, int x, int y, double &rho, double &ux, double &uy,
+                                            double &axx, double &axy, double &ayy) {
+    T f[Q];
+    load_node<T, PULL>(p, x, y, f);
+    double g[Q];
+    static_for<0, Q>([&](auto I) { g[decltype(I)::value] = (double)f[decltype(I)::value]; });
+    rho_u<double>(g, rho, ux, uy);
+    // a_bar_2 = sum(f[idx] * hermite(Val{2}, c_idx, q))  (moments.jl:27-28, 90-92), left fold
+    const LatConst<double> &c = c_lat64;
+    axx = g[0] * c.H2[0][0]; axy = g[0] * c.H2[0][1]; ayy = g[0] * c.H2[0][2];
+    static_for<1, Q>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        axx = axx + g[i] * c.H2[i][0];
+        axy = axy + g[i] * c.H2[i][1];
+        ayy = ayy + g[i] * c.H2[i][2];
+    });
+}
+
+template <typename T, bool PULL>
+__global__ void __launch_bounds__(256) k_moments(const __grid_constant__ KParams<T> p, const MomentsOut m) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= p.nx) return;
+    for (int y = blockIdx.y * blockDim.y + threadIdx.y; y < p.nyl; y += gridDim.y * blockDim.y) {
+        double rho, ux, uy, axx, axy, ayy;
+        node_fields<T, PULL>(p, x, y, rho, ux, uy, axx, axy, ayy);
+        const long long n = (long long)y * p.nx + x;
+        if (m.rho) m.rho[n] = rho;
+        if (m.ux) m.ux[n] = ux;
+        if (m.uy) m.uy[n] = uy;
+        if (m.p) {  // moments.jl:31-32
+            if constexpr (L::UNIT_PRESSURE) m.p[n] = 1.0;
+            else m.p[n] = ((axx + ayy) - rho * ((ux * ux + uy * uy) - 2)) / 2;
+        }
+        if (m.p_track || m.sxx || m.sxy || m.syy) {
+            const double tau = m.tau_visc;
+            const double exx = rho * (ux * ux + 0.0), exy = rho * (ux * uy), eyy = rho * (uy * uy + 0.0);
+            const double den = 1 + 1 / (2 * tau);
+            if (m.p_track) {  // track_hydrodynamic_errors.jl:153,173,181
+                const double bxx = (axx + (1 / (2 * tau)) * exx) / den;
+                const double byy = (ayy + (1 / (2 * tau)) * eyy) / den;
+                const double Pxx = bxx - rho * (ux * ux - 1);
+                const double Pyy = byy - rho * (uy * uy - 1);
+                m.p_track[n] = (Pxx + Pyy) / 2;
+            }
+            // deviatoric_tensor(q, tau, f, rho, u)  moments.jl:81-96
+            const double sxx = (axx - exx) / den, sxy = (axy - exy) / den, syy = (ayy - eyy) / den;
+            const double tr = (sxx + syy) / 2;
+            if (m.sxx) m.sxx[n] = sxx - tr;
+            if (m.sxy) m.sxy[n] = sxy;
+            if (m.syy) m.syy[n] = syy - tr;
+        }
+    }
+}
+
+// deterministic two-stage reduction of up to 4 per-node quantities
+template <typename T, bool PULL>
+__global__ void __launch_bounds__(256) k_reduce(const __grid_constant__ KParams<T> p, const ReduceArgs ra) {
+    double acc[4] = {0, 0, 0, 0};
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    for (int y = blockIdx.y * blockDim.y + threadIdx.y; y < p.nyl; y += gridDim.y * blockDim.y)
+        for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < p.nx; x += gridDim.x * blockDim.x) {
+            double rho, ux, uy, axx, axy, ayy;
+            node_fields<T, PULL>(p, x, y, rho, ux, uy, axx, axy, ayy);
+            const long long n = (long long)y * p.nx + x;
+            if (ra.kind == LBM_REDUCE_MEAN_UX) {
+                acc[0] += ux; acc[1] += 1.0; acc[2] += (ux != ux) ? 1.0 : 0.0;
+            } else if (ra.kind == LBM_REDUCE_VELOCITY_CHANGE) {
+                const long long N = (long long)p.nyl * p.nx;
+                const double ox = ra.u_old[n], oy = ra.u_old[N + n];
+                acc[0] += ((ux - ox) * (ux - ox) + (uy - oy) * (uy - oy));
+                acc[1] += ox * ox + oy * oy;
+                ra.u_old[n] = ux; ra.u_old[N + n] = uy;
+            } else {
+                acc[0] += rho; acc[1] += rho * (ux + uy); acc[2] += rho * (ux * ux + uy * uy);
+            }
+        }
+    __shared__ double sm[4][8];
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        double v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) sm[k][warp] = v;
+    }
+    __syncthreads();
+    if (tid < 4) {
+        const int nw = (blockDim.x * blockDim.y + 31) >> 5;
+        double v = 0;
+        for (int w = 0; w < nw; ++w) v += sm[tid][w];
+        ra.partials[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 4 + tid] = v;
+    }
+}
+
+__global__ void k_reduce_final(const ReduceArgs ra) {
+    const int k = threadIdx.x;
+    if (k < 4) {
+        double v = 0;
+        for (int b = 0; b < ra.nblocks; ++b) v += ra.partials[(size_t)b * 4 + k];
+        ra.out[k] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+static inline void pick_block(int nx, dim3 &block) {
+    int bx = 32;
+    while (bx < 256 && bx < nx) bx <<= 1;
+    block = dim3(bx, 256 / bx, 1);
+}
+
+template <typename T>
+static inline dim3 grid_for(const KParams<T> &p, const dim3 &block, int rows, int cols) {
+    unsigned gy = (rows + block.y - 1) / block.y;
+    if (gy > 65535u) gy = 65535u;
+    if (gy == 0) gy = 1;
+    return dim3((cols + block.x - 1) / block.x, gy, 1);
+}
+
+template <typename T>
+static void launch_step(int cm, bool pull, const KParams<T> &p, long long step, int variant, cudaStream_t s) {
+    (void)variant;
+    if (p.nrows <= 0) return;
+    dim3 block; pick_block(p.nx, block);
+    dim3 grid = grid_for(p, block, p.nrows, p.nx);
+#define LBM_LAUNCH(CM)                                                         \
+    if (pull) k_step<CM, T, true><<<grid, block, 0, s>>>(p, step);             \
+    else k_step<CM, T, false><<<grid, block, 0, s>>>(p, step);
+    switch (cm) {
+    case LBM_SRT: LBM_LAUNCH(LBM_SRT) break;
+    case LBM_TRT: LBM_LAUNCH(LBM_TRT) break;
+    default: LBM_LAUNCH(LBM_MRT) break;
+    }
+#undef LBM_LAUNCH
+}
+
+template <typename T>
+static void launch_stream(const KParams<T> &p, cudaStream_t s) {
+    if (p.nrows <= 0) return;
+    dim3 block; pick_block(p.nx, block);
+    k_stream<T><<<grid_for(p, block, p.nrows, p.nx), block, 0, s>>>(p);
+}
+template <typename T>
+static void launch_bcs(const KParams<T> &p, cudaStream_t s) {
+    if (p.nrows <= 0 || p.nbc == 0) return;
+    dim3 block; pick_block(p.nx, block);
+    k_bcs<T><<<grid_for(p, block, p.nrows, p.nx), block, 0, s>>>(p);
+}
+template <typename T>
+static void launch_ghosts(const KParams<T> &p, cudaStream_t s) {
+    dim3 block; pick_block(p.nx + 2 * H, block);
+    k_ghosts<T><<<grid_for(p, block, p.nyl + 2 * H, p.nx + 2 * H), block, 0, s>>>(p);
+}
+template <typename T>
+static void launch_moments(bool pull, const KParams<T> &p, const MomentsOut &m, cudaStream_t s) {
+    dim3 block; pick_block(p.nx, block);
+    dim3 grid = grid_for(p, block, p.nyl, p.nx);
+    if (pull) k_moments<T, true><<<grid, block, 0, s>>>(p, m);
+    else k_moments<T, false><<<grid, block, 0, s>>>(p, m);
+}
+template <typename T>
+static void launch_reduce(bool pull, const KParams<T> &p, const ReduceArgs &r, cudaStream_t s) {
+    dim3 block; pick_block(p.nx, block);
+    dim3 grid = grid_for(p, block, p.nyl, p.nx);
+    // cap the number of partial blocks; the kernel grid-strides
+    while ((long long)grid.x * grid.y > r.nblocks && grid.y > 1) grid.y = (grid.y + 1) / 2;
+    while ((long long)grid.x * grid.y > r.nblocks && grid.x > 1) grid.x = (grid.x + 1) / 2;
+    ReduceArgs ra = r;
+    ra.nblocks = grid.x * grid.y;
+    if (pull) k_reduce<T, true><<<grid, block, 0, s>>>(p, ra);
+    else k_reduce<T, false><<<grid, block, 0, s>>>(p, ra);
+    k_reduce_final<<<1, 32, 0, s>>>(ra);
+}
+
+static const Ops ops = {
+    LBM_LATTICE, LBM_FAST,
+    &launch_step<double>, nullptr,
+    &launch_stream<double>, nullptr,
+    &launch_bcs<double>, nullptr,
+    &launch_ghosts<double>, nullptr,
+    &launch_moments<double>, nullptr,
+    &launch_reduce<double>, nullptr,
+    nullptr, nullptr,
+    &init_constants,
+};
+
+}  // namespace LBM_NS
+
+#define LBM_GETTER2(a, b) get_ops_##a##_##b
+#define LBM_GETTER(a, b) LBM_GETTER2(a, b)
+const Ops *LBM_GETTER(LBM_LATTICE, LBM_FAST)() { return &LBM_NS::ops; }
+
+}  // namespace lbm

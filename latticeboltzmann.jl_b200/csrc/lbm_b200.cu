@@ -1,0 +1,841 @@
+// liblbm_b200.so -- context management and the C ABI declared in include/lbm_b200.h.
+// Kernels live in kernels_inst.cu (one instance per <lattice, arithmetic mode>).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types only; the library is dlopen'ed when world > 1
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <type_traits>
+#include "common.h"
+
+namespace lbm {
+#define LBM_DECL(a, b) const Ops *get_ops_##a##_##b();
+#define LBM_DECL_BOTH(a) LBM_DECL(a, 0) LBM_DECL(a, 1)
+LBM_DECL_BOTH(LBM_D2Q4) LBM_DECL_BOTH(LBM_D2Q5) LBM_DECL_BOTH(LBM_D2Q9) LBM_DECL_BOTH(LBM_D2Q13)
+LBM_DECL_BOTH(LBM_D2Q17) LBM_DECL_BOTH(LBM_D2Q21) LBM_DECL_BOTH(LBM_D2Q37)
+
+const Ops *get_ops(int lattice, int arith) {
+#define LBM_CASE(a) case a: return arith ? get_ops_##a##_1() : get_ops_##a##_0();
+    switch (lattice) {
+        LBM_CASE(LBM_D2Q4) LBM_CASE(LBM_D2Q5) LBM_CASE(LBM_D2Q9) LBM_CASE(LBM_D2Q13)
+        LBM_CASE(LBM_D2Q17) LBM_CASE(LBM_D2Q21) LBM_CASE(LBM_D2Q37)
+    default: return nullptr;
+    }
+}
+}  // namespace lbm
+
+using namespace lbm;
+
+// ----------------------------------------------------------------------------------------------
+// errors
+// ----------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) return fail(LBM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// ----------------------------------------------------------------------------------------------
+// NCCL, loaded lazily
+// ----------------------------------------------------------------------------------------------
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int load_nccl() {
+    if (g_nccl.handle) return 0;
+    const char *names[] = {getenv("LBM_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    void *h = nullptr;
+    for (const char *n : names) {
+        if (!n) continue;
+        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) return fail(LBM_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+#define SYM(field, name)                                                     \
+    *(void **)(&g_nccl.field) = dlsym(h, name);                              \
+    if (!g_nccl.field) return fail(LBM_ERR_NCCL, "missing NCCL symbol %s", name);
+    SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
+    SYM(Send, "ncclSend") SYM(Recv, "ncclRecv") SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd")
+    SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    g_nccl.handle = h;
+    return 0;
+}
+
+#define NC(call)                                                                                    \
+    do {                                                                                            \
+        ncclResult_t r_ = (call);                                                                   \
+        if (r_ != ncclSuccess) return fail(LBM_ERR_NCCL, "%s failed: %s", #call, g_nccl.GetErrorString(r_)); \
+    } while (0)
+
+// ----------------------------------------------------------------------------------------------
+// context
+// ----------------------------------------------------------------------------------------------
+enum { ST_STREAM = 0, ST_COLLIDED = 1 };
+
+struct lbm_ctx {
+    lbm_desc desc;
+    LatticeInfo li;
+    const Ops *ops = nullptr;
+    int nyl = 0, y0 = 0;
+    int gx = 0, gy = 0;
+    long long pitch = 0, plane = 0;
+    size_t elt = 8;
+    void *buf[2] = {nullptr, nullptr};
+    int cur = 0;         // buffer holding the newest state
+    int state = ST_STREAM;
+    bool have_coll = false;  // buf[1-cur] holds f_collision matching f_stream in buf[cur]
+    bool resume_ok = false;  // ... and its ghosts/halos are valid, so the next step may pull from it
+    cudaStream_t stream = nullptr, comm_stream = nullptr;
+    cudaEvent_t ev_b = nullptr, ev_c = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_u0 = nullptr, ev_u1 = nullptr;
+    bool comm_pending = false;
+    // force
+    int force_mode = 0;
+    double fx = 0, fy = 0;
+    void *field = nullptr;
+    void *sep_fx = nullptr, *sep_fy = nullptr;
+    long long sep_t0 = 0;
+    int sep_n = 0;
+    // diagnostics
+    double *partials = nullptr, *red_out = nullptr, *u_old = nullptr;
+    int red_blocks = 2048;
+    // multi-GPU
+    ncclComm_t comm = nullptr;
+    int up = 0, down = 0;
+    long long launches = 0;
+    bool timed = false;
+    int opt_variant = 0;
+    int opt_overlap = 1;
+};
+
+template <typename T>
+static T *origin(const lbm_ctx *c, int b) {
+    return reinterpret_cast<T *>(c->buf[b]) + (long long)c->gy * c->pitch + c->gx;
+}
+
+template <typename T>
+static KParams<T> make_params(const lbm_ctx *c, int src, int dst) {
+    KParams<T> p;
+    memset(&p, 0, sizeof(p));
+    p.src = origin<T>(c, src);
+    p.dst = origin<T>(c, dst);
+    p.aux = nullptr;
+    p.pitch = c->pitch;
+    p.plane = c->plane;
+    p.nx = c->desc.nx;
+    p.nyl = c->nyl;
+    p.y0g = c->y0;
+    p.nyg = c->desc.ny;
+    p.row_a0 = 0; p.row_an = c->nyl; p.row_b0 = 0; p.nrows = c->nyl;
+    p.wrap_y = c->desc.world == 1;
+    const double *tau = c->desc.tau;
+    const double css = c->li.css;
+    switch (c->desc.collision) {
+    case LBM_SRT:
+        p.c[0] = (T)(1 - 1 / tau[0]); p.c[1] = (T)(1 / tau[0]); p.shift = (T)tau[0];
+        break;
+    case LBM_TRT:
+        p.c[0] = (T)(-(1 / tau[0])); p.c[1] = (T)(1 / tau[1]); p.shift = (T)tau[1];
+        break;
+    default: {
+        static const double fact[5] = {1, 1, 2, 6, 24};
+        for (int n = 2; n <= c->li.N; ++n) {
+            const double tn = tau[n - 1];
+            p.c[2 * n] = (T)(1 - 1 / tn);
+            p.c[2 * n + 1] = (T)(1 / tn);
+            p.kn[n] = (T)(std::pow(css, (double)n) / fact[n]);
+            p.mrt_skip[n] = (tn == 1.0);
+        }
+        p.shift = (T)(c->desc.ntau >= 2 ? tau[1] : 0.0);
+        break;
+    }
+    }
+    p.force_mode = c->force_mode;
+    p.fx = (T)c->fx; p.fy = (T)c->fy;
+    p.field = (const T *)c->field;
+    p.sep_fx = (const T *)c->sep_fx; p.sep_fy = (const T *)c->sep_fy;
+    p.sep_t0 = c->sep_t0;
+    p.nbc = c->desc.n_bcs;
+    for (int b = 0; b < p.nbc; ++b) {
+        const lbm_bc &s = c->desc.bcs[b];
+        BCd &d = p.bc[b];
+        d.kind = s.kind; d.dir = s.direction;
+        d.x0 = s.x0; d.x1 = s.x1; d.y0 = s.y0; d.y1 = s.y1;
+        d.ax = s.rho * s.u[0]; d.ay = s.rho * s.u[1];  // equilibrium_coefficient(Val{1}) hermite.jl:41-43
+    }
+    return p;
+}
+
+static bool is64(const lbm_ctx *c) { return c->desc.dtype == LBM_F64; }
+
+// ----------------------------------------------------------------------------------------------
+// halo exchange (y-slabs): rows of populations moving up go to `up`, moving down to `down`
+// ----------------------------------------------------------------------------------------------
+static int exchange_halos(lbm_ctx *c, int b, cudaStream_t s) {
+    if (c->desc.world == 1) return 0;
+    const size_t es = c->elt;
+    char *base = (char *)c->buf[b];
+    auto row = [&](int i, int y) {  // address of (plane i, local row y, x = -gx)
+        return base + ((size_t)i * c->plane + (size_t)(y + c->gy) * c->pitch) * es;
+    };
+    const ncclDataType_t dt = is64(c) ? ncclDouble : ncclFloat;
+    NC(g_nccl.GroupStart());
+    // sends: first everything going up, then everything going down (same order on every rank,
+    // which keeps send/recv matching correct when up == down, i.e. world == 2)
+    for (int i = 0; i < c->li.Q; ++i) {
+        const int cy = c->li.cy[i];
+        if (cy > 0) NC(g_nccl.Send(row(i, c->nyl - cy), (size_t)cy * c->pitch, dt, c->up, c->comm, s));
+    }
+    for (int i = 0; i < c->li.Q; ++i) {
+        const int cy = c->li.cy[i];
+        if (cy < 0) NC(g_nccl.Send(row(i, 0), (size_t)(-cy) * c->pitch, dt, c->down, c->comm, s));
+    }
+    // receives: what `down` sent up lands in my bottom ghost rows, what `up` sent down in my top ghost rows
+    for (int i = 0; i < c->li.Q; ++i) {
+        const int cy = c->li.cy[i];
+        if (cy > 0) NC(g_nccl.Recv(row(i, -cy), (size_t)cy * c->pitch, dt, c->down, c->comm, s));
+    }
+    for (int i = 0; i < c->li.Q; ++i) {
+        const int cy = c->li.cy[i];
+        if (cy < 0) NC(g_nccl.Recv(row(i, c->nyl), (size_t)(-cy) * c->pitch, dt, c->up, c->comm, s));
+    }
+    NC(g_nccl.GroupEnd());
+    c->launches += 1;
+    return 0;
+}
+
+// main stream waits until the last posted exchange has landed
+static int wait_comm(lbm_ctx *c) {
+    if (c->comm_pending) {
+        CU(cudaStreamWaitEvent(c->stream, c->ev_c, 0));
+        c->comm_pending = false;
+    }
+    return 0;
+}
+
+static int post_exchange(lbm_ctx *c, int b) {
+    if (c->desc.world == 1) return 0;
+    CU(cudaEventRecord(c->ev_b, c->stream));
+    CU(cudaStreamWaitEvent(c->comm_stream, c->ev_b, 0));
+    int rc = exchange_halos(c, b, c->comm_stream);
+    if (rc) return rc;
+    CU(cudaEventRecord(c->ev_c, c->comm_stream));
+    c->comm_pending = true;
+    return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// kernel sequencing
+// ----------------------------------------------------------------------------------------------
+template <typename T>
+static void run_step(lbm_ctx *c, bool pull, const KParams<T> &p, long long step) {
+    if (std::is_same<T, double>::value) c->ops->step64(c->desc.collision, pull, reinterpret_cast<const KParams<double> &>(p), step, c->opt_variant, c->stream);
+    else c->ops->step32(c->desc.collision, pull, reinterpret_cast<const KParams<float> &>(p), step, c->opt_variant, c->stream);
+    c->launches += 1;
+}
+
+// collide buf[cur] (f_stream) -> buf[1-cur] (f_collision, with ghosts + halos)
+template <typename T>
+static int do_collide(lbm_ctx *c, long long step) {
+    KParams<T> p = make_params<T>(c, c->cur, 1 - c->cur);
+    run_step<T>(c, false, p, step);
+    CU(cudaGetLastError());
+    return post_exchange(c, 1 - c->cur);
+}
+
+// one fused step: buf[src] holds post-collision populations of the previous step
+template <typename T>
+static int do_fused(lbm_ctx *c, int src, int dst, long long step) {
+    KParams<T> p = make_params<T>(c, src, dst);
+    const int H = c->li.H;
+    if (c->desc.world == 1) {
+        run_step<T>(c, true, p, step);
+    } else if (!c->opt_overlap || c->nyl < 2 * H + 1) {
+        int rc = wait_comm(c);
+        if (rc) return rc;
+        run_step<T>(c, true, p, step);
+    } else {
+        // interior rows need no halo -> launch them first, then wait for the previous exchange and
+        // do the 2H boundary rows; their exchange then overlaps the next step's interior.
+        KParams<T> pi = p;
+        pi.row_a0 = H; pi.row_an = c->nyl - 2 * H; pi.nrows = pi.row_an;
+        run_step<T>(c, true, pi, step);
+        int rc = wait_comm(c);
+        if (rc) return rc;
+        KParams<T> pb = p;
+        pb.row_a0 = 0; pb.row_an = H; pb.row_b0 = c->nyl - H; pb.nrows = 2 * H;
+        run_step<T>(c, true, pb, step);
+    }
+    CU(cudaGetLastError());
+    return post_exchange(c, dst);
+}
+
+// f_stream := (stream + BCs)(f_collision) into the other buffer; afterwards cur = f_stream
+template <typename T>
+static int do_materialize(lbm_ctx *c) {
+    if (c->state != ST_COLLIDED) return 0;
+    int rc = wait_comm(c);
+    if (rc) return rc;
+    KParams<T> p = make_params<T>(c, c->cur, 1 - c->cur);
+    if (std::is_same<T, double>::value) c->ops->stream64(reinterpret_cast<const KParams<double> &>(p), c->stream);
+    else c->ops->stream32(reinterpret_cast<const KParams<float> &>(p), c->stream);
+    c->launches += 1;
+    CU(cudaGetLastError());
+    c->cur = 1 - c->cur;
+    c->state = ST_STREAM;
+    c->have_coll = true;
+    c->resume_ok = true;
+    return 0;
+}
+
+static int materialize(lbm_ctx *c) { return is64(c) ? do_materialize<double>(c) : do_materialize<float>(c); }
+
+template <typename T>
+static int do_steps(lbm_ctx *c, long long t0, long long n) {
+    for (long long k = 0; k < n; ++k) {
+        const long long t = t0 + k;
+        int rc;
+        if (c->state == ST_STREAM) {
+            if (c->resume_ok && c->have_coll) {
+                // buf[1-cur] = f_collision of the previous step with valid ghosts: pull from it
+                rc = do_fused<T>(c, 1 - c->cur, c->cur, t);
+            } else {
+                rc = do_collide<T>(c, t);
+                c->cur = 1 - c->cur;
+            }
+            c->state = ST_COLLIDED;
+            c->have_coll = false;
+            c->resume_ok = false;
+        } else {
+            rc = do_fused<T>(c, c->cur, 1 - c->cur, t);
+            c->cur = 1 - c->cur;
+        }
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// C ABI
+// ----------------------------------------------------------------------------------------------
+extern "C" {
+
+int lbm_abi_version(void) { return LBM_ABI_VERSION; }
+const char *lbm_last_error(void) { return g_err.c_str(); }
+
+int lbm_lattice_info(int32_t lattice, int32_t *q, int32_t *cx, int32_t *cy, double *w, double *css,
+                     int32_t *opposite, int32_t *eq_order, int32_t *hermite_order, int32_t *halo) {
+    LatticeInfo li;
+    if (!lattice_info(lattice, li)) return fail(LBM_ERR_INVALID, "unknown lattice id %d", lattice);
+    if (q) *q = li.Q;
+    for (int i = 0; i < LBM_MAX_Q; ++i) {
+        if (cx) cx[i] = li.cx[i];
+        if (cy) cy[i] = li.cy[i];
+        if (w) w[i] = li.w[i];
+        if (opposite) opposite[i] = li.opp[i];
+    }
+    if (css) *css = li.css;
+    if (eq_order) *eq_order = li.eq_order;
+    if (hermite_order) *hermite_order = li.N;
+    if (halo) *halo = li.H;
+    return 0;
+}
+
+int lbm_nccl_unique_id(uint8_t id[LBM_NCCL_ID_BYTES]) {
+    int rc = load_nccl();
+    if (rc) return rc;
+    ncclUniqueId uid;
+    static_assert(sizeof(ncclUniqueId) == LBM_NCCL_ID_BYTES, "ncclUniqueId size");
+    NC(g_nccl.GetUniqueId(&uid));
+    memcpy(id, &uid, sizeof(uid));
+    return 0;
+}
+
+void lbm_destroy(lbm_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->desc.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    for (void *p : {c->buf[0], c->buf[1], c->field, c->sep_fx, c->sep_fy, (void *)c->partials, (void *)c->red_out, (void *)c->u_old})
+        if (p) cudaFree(p);
+    for (cudaEvent_t e : {c->ev_b, c->ev_c, c->ev_t0, c->ev_t1, c->ev_u0, c->ev_u1})
+        if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
+    delete c;
+}
+
+int lbm_create(const lbm_desc *d, lbm_ctx **out) {
+    if (!d || !out) return fail(LBM_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (d->abi_version != LBM_ABI_VERSION) return fail(LBM_ERR_INVALID, "abi_version %d != %d", d->abi_version, LBM_ABI_VERSION);
+    if (d->nx < 1 || d->ny < 1) return fail(LBM_ERR_INVALID, "grid %dx%d", d->nx, d->ny);
+    LatticeInfo li;
+    if (!lattice_info(d->lattice, li)) return fail(LBM_ERR_INVALID, "unknown lattice id %d", d->lattice);
+    if (d->dtype != LBM_F64 && d->dtype != LBM_F32) return fail(LBM_ERR_INVALID, "dtype %d", d->dtype);
+    if (d->collision < LBM_SRT || d->collision > LBM_MRT) return fail(LBM_ERR_INVALID, "collision %d", d->collision);
+    if (d->arith != LBM_ARITH_EXACT && d->arith != LBM_ARITH_FAST) return fail(LBM_ERR_INVALID, "arith %d", d->arith);
+    const int need_tau = d->collision == LBM_SRT ? 1 : (d->collision == LBM_TRT ? 2 : li.N);
+    if (d->ntau < need_tau || d->ntau > LBM_MAX_TAU) return fail(LBM_ERR_INVALID, "ntau %d (need >= %d)", d->ntau, need_tau);
+    for (int i = 0; i < d->ntau; ++i)
+        if (!(d->tau[i] == d->tau[i]) || d->tau[i] == 0.0) return fail(LBM_ERR_INVALID, "tau[%d] = %g", i, d->tau[i]);
+    if (d->n_bcs < 0 || d->n_bcs > LBM_MAX_BCS) return fail(LBM_ERR_INVALID, "n_bcs %d", d->n_bcs);
+    for (int b = 0; b < d->n_bcs; ++b) {
+        const lbm_bc &bc = d->bcs[b];
+        if (bc.direction < LBM_NORTH || bc.direction > LBM_WEST) return fail(LBM_ERR_INVALID, "bc %d: direction %d", b, bc.direction);
+        if (bc.kind == LBM_BC_MOVING_WALL) {
+            // only apply!(::MovingWall{<:North}, ...) exists (moving_wall.jl:17)
+            if (bc.direction != LBM_NORTH) return fail(LBM_ERR_UNSUPPORTED, "bc %d: MovingWall is only defined for North", b);
+        } else if (bc.kind != LBM_BC_BOUNCE_BACK) {
+            return fail(LBM_ERR_INVALID, "bc %d: kind %d", b, bc.kind);
+        }
+    }
+    if (d->world < 1 || d->rank < 0 || d->rank >= d->world) return fail(LBM_ERR_INVALID, "rank %d / world %d", d->rank, d->world);
+    const Ops *ops = get_ops(d->lattice, d->arith);
+    if (!ops) return fail(LBM_ERR_UNSUPPORTED, "no kernels for lattice %d", d->lattice);
+    if (d->dtype == LBM_F32 && !ops->step32) return fail(LBM_ERR_UNSUPPORTED, "Float32 kernels not built");
+
+    lbm_ctx *c = new lbm_ctx();
+    c->desc = *d;
+    c->li = li;
+    c->ops = ops;
+    // y-slabs: rows split as evenly as possible, the first (ny % world) ranks get one extra
+    const int base = d->ny / d->world, rem = d->ny % d->world;
+    c->nyl = base + (d->rank < rem ? 1 : 0);
+    c->y0 = d->rank * base + (d->rank < rem ? d->rank : rem);
+    if (d->world > 1 && c->nyl < li.H) {
+        delete c;
+        return fail(LBM_ERR_INVALID, "slab of %d rows is thinner than the halo (%d)", c->nyl, li.H);
+    }
+    c->elt = d->dtype == LBM_F64 ? 8 : 4;
+    const int align = (int)(128 / c->elt);
+    c->gx = d->nx >= 128 ? align : 4;
+    c->gy = li.H;
+    c->pitch = ((long long)d->nx + 2 * c->gx + align - 1) / align * align;
+    c->plane = c->pitch * (c->nyl + 2 * c->gy);
+    c->up = (d->rank + 1) % d->world;
+    c->down = (d->rank + d->world - 1) % d->world;
+
+    cudaError_t e = cudaSetDevice(d->device);
+    if (e != cudaSuccess) { delete c; return fail(LBM_ERR_CUDA, "cudaSetDevice(%d): %s", d->device, cudaGetErrorString(e)); }
+    int rc = 0;
+    auto bail = [&](int code) { lbm_destroy(c); return code; };
+    if (ops->init_constants() != 0) return bail(fail(LBM_ERR_CUDA, "constant upload failed: %s", cudaGetErrorString(cudaGetLastError())));
+    const size_t bytes = (size_t)li.Q * c->plane * c->elt;
+    for (int b = 0; b < 2; ++b) {
+        e = cudaMalloc(&c->buf[b], bytes);
+        if (e != cudaSuccess) return bail(fail(LBM_ERR_NOMEM, "cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString(e)));
+        cudaMemset(c->buf[b], 0, bytes);
+    }
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_c, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreate(&c->ev_t0) != cudaSuccess || cudaEventCreate(&c->ev_t1) != cudaSuccess ||
+        cudaEventCreate(&c->ev_u0) != cudaSuccess || cudaEventCreate(&c->ev_u1) != cudaSuccess)
+        return bail(fail(LBM_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError())));
+    if (cudaMalloc(&c->partials, (size_t)c->red_blocks * 4 * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&c->red_out, 4 * sizeof(double)) != cudaSuccess)
+        return bail(fail(LBM_ERR_NOMEM, "reduction buffers"));
+    if (d->world > 1) {
+        rc = load_nccl();
+        if (rc) return bail(rc);
+        ncclUniqueId uid;
+        memcpy(&uid, d->nccl_id, sizeof(uid));
+        ncclResult_t r = g_nccl.CommInitRank(&c->comm, d->world, uid, d->rank);
+        if (r != ncclSuccess) return bail(fail(LBM_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString(r)));
+    }
+    cudaDeviceSynchronize();
+    *out = c;
+    return 0;
+}
+
+int lbm_local_rows(const lbm_ctx *c, int32_t *y0, int32_t *ny_local) {
+    if (!c) return fail(LBM_ERR_INVALID, "null context");
+    if (y0) *y0 = c->y0;
+    if (ny_local) *ny_local = c->nyl;
+    return 0;
+}
+
+static int refresh_ghosts(lbm_ctx *c, int b) {
+    if (is64(c)) { KParams<double> p = make_params<double>(c, b, b); c->ops->ghosts64(p, c->stream); }
+    else { KParams<float> p = make_params<float>(c, b, b); c->ops->ghosts32(p, c->stream); }
+    c->launches += 1;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+static int upload_buffer(lbm_ctx *c, int b, const double *f) {
+    const int nx = c->desc.nx, Q = c->li.Q;
+    if (is64(c)) {
+        double *o = origin<double>(c, b);
+        for (int i = 0; i < Q; ++i)
+            CU(cudaMemcpy2DAsync(o + (size_t)i * c->plane, c->pitch * 8, f + (size_t)i * c->nyl * nx, (size_t)nx * 8,
+                                 (size_t)nx * 8, c->nyl, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        double *stage = nullptr;
+        CU(cudaMalloc(&stage, (size_t)c->nyl * nx * 8));
+        KParams<float> p = make_params<float>(c, b, b);
+        for (int i = 0; i < Q; ++i) {
+            CU(cudaMemcpyAsync(stage, f + (size_t)i * c->nyl * nx, (size_t)c->nyl * nx * 8, cudaMemcpyHostToDevice, c->stream));
+            c->ops->import32(p, stage, i, c->stream);
+            c->launches += 1;
+        }
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaFree(stage));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int lbm_upload_f(lbm_ctx *c, const double *f) {
+    if (!c || !f) return fail(LBM_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(c->desc.device));
+    int rc = wait_comm(c);
+    if (rc) return rc;
+    rc = upload_buffer(c, c->cur, f);
+    if (rc) return rc;
+    c->state = ST_STREAM;
+    c->have_coll = false;
+    c->resume_ok = false;
+    return 0;
+}
+
+int lbm_upload_f_collision(lbm_ctx *c, const double *f) {
+    if (!c || !f) return fail(LBM_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(c->desc.device));
+    int rc = materialize(c);
+    if (rc) return rc;
+    rc = wait_comm(c);
+    if (rc) return rc;
+    rc = upload_buffer(c, 1 - c->cur, f);
+    if (rc) return rc;
+    rc = refresh_ghosts(c, 1 - c->cur);
+    if (rc) return rc;
+    rc = post_exchange(c, 1 - c->cur);
+    if (rc) return rc;
+    c->have_coll = true;
+    c->resume_ok = false;
+    return 0;
+}
+
+static int download_buffer(lbm_ctx *c, int b, double *f) {
+    const int nx = c->desc.nx, Q = c->li.Q;
+    if (is64(c)) {
+        const double *o = origin<double>(c, b);
+        for (int i = 0; i < Q; ++i)
+            CU(cudaMemcpy2DAsync(f + (size_t)i * c->nyl * nx, (size_t)nx * 8, o + (size_t)i * c->plane, c->pitch * 8,
+                                 (size_t)nx * 8, c->nyl, cudaMemcpyDeviceToHost, c->stream));
+    } else {
+        double *stage = nullptr;
+        CU(cudaMalloc(&stage, (size_t)c->nyl * nx * 8));
+        KParams<float> p = make_params<float>(c, b, b);
+        for (int i = 0; i < Q; ++i) {
+            c->ops->export32(p, stage, i, c->stream);
+            c->launches += 1;
+            CU(cudaMemcpyAsync(f + (size_t)i * c->nyl * nx, stage, (size_t)c->nyl * nx * 8, cudaMemcpyDeviceToHost, c->stream));
+        }
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaFree(stage));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int lbm_download_f(lbm_ctx *c, double *f) {
+    if (!c || !f) return fail(LBM_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(c->desc.device));
+    int rc = materialize(c);
+    if (rc) return rc;
+    return download_buffer(c, c->cur, f);
+}
+
+int lbm_download_f_collision(lbm_ctx *c, double *f) {
+    if (!c || !f) return fail(LBM_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(c->desc.device));
+    if (c->state == ST_COLLIDED) {
+        int rc = wait_comm(c);
+        if (rc) return rc;
+        return download_buffer(c, c->cur, f);
+    }
+    if (!c->have_coll) return fail(LBM_ERR_STATE, "no f_collision: collide! has not run since the last upload");
+    return download_buffer(c, 1 - c->cur, f);
+}
+
+static void free_force(lbm_ctx *c) {
+    cudaStreamSynchronize(c->stream);
+    for (void **p : {&c->field, &c->sep_fx, &c->sep_fy})
+        if (*p) { cudaFree(*p); *p = nullptr; }
+    c->force_mode = 0;
+}
+
+// host double array -> device array of the context's element type
+static int upload_as_elt(lbm_ctx *c, const double *h, size_t n, void **dev) {
+    CU(cudaMalloc(dev, n * c->elt));
+    if (is64(c)) {
+        CU(cudaMemcpy(*dev, h, n * 8, cudaMemcpyHostToDevice));
+    } else {
+        std::vector<float> tmp(n);
+        for (size_t k = 0; k < n; ++k) tmp[k] = (float)h[k];
+        CU(cudaMemcpy(*dev, tmp.data(), n * 4, cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+int lbm_set_force_none(lbm_ctx *c) {
+    if (!c) return fail(LBM_ERR_INVALID, "null context");
+    CU(cudaSetDevice(c->desc.device));
+    free_force(c);
+    return 0;
+}
+
+int lbm_set_force_uniform(lbm_ctx *c, double fx, double fy) {
+    if (!c) return fail(LBM_ERR_INVALID, "null context");
+    CU(cudaSetDevice(c->desc.device));
+    if (c->desc.collision == LBM_MRT && c->desc.ntau < 2) return fail(LBM_ERR_INVALID, "MRT forcing needs tau[1] (mrt.jl:94)");
+    free_force(c);
+    c->force_mode = 1; c->fx = fx; c->fy = fy;
+    return 0;
+}
+
+int lbm_set_force_field(lbm_ctx *c, const double *F) {
+    if (!c || !F) return fail(LBM_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(c->desc.device));
+    if (c->desc.collision == LBM_MRT && c->desc.ntau < 2) return fail(LBM_ERR_INVALID, "MRT forcing needs tau[1] (mrt.jl:94)");
+    free_force(c);
+    int rc = upload_as_elt(c, F, (size_t)2 * c->nyl * c->desc.nx, &c->field);
+    if (rc) return rc;
+    c->force_mode = 2;
+    return 0;
+}
+
+int lbm_set_force_separable(lbm_ctx *c, int64_t t0, int32_t nsteps, const double *fx_of_y, const double *fy_of_x) {
+    if (!c || !fx_of_y || !fy_of_x || nsteps < 1) return fail(LBM_ERR_INVALID, "bad argument");
+    CU(cudaSetDevice(c->desc.device));
+    if (c->desc.collision == LBM_MRT && c->desc.ntau < 2) return fail(LBM_ERR_INVALID, "MRT forcing needs tau[1] (mrt.jl:94)");
+    free_force(c);
+    int rc = upload_as_elt(c, fx_of_y, (size_t)nsteps * c->nyl, &c->sep_fx);
+    if (rc) return rc;
+    rc = upload_as_elt(c, fy_of_x, (size_t)nsteps * c->desc.nx, &c->sep_fy);
+    if (rc) return rc;
+    c->sep_t0 = t0; c->sep_n = nsteps;
+    c->force_mode = 3;
+    return 0;
+}
+
+static int check_force_window(lbm_ctx *c, int64_t t0, int64_t n) {
+    if (c->force_mode == 3 && (t0 < c->sep_t0 || t0 + n > c->sep_t0 + c->sep_n))
+        return fail(LBM_ERR_STATE, "steps [%lld, %lld) outside the separable force table [%lld, %lld)", (long long)t0,
+                    (long long)(t0 + n), c->sep_t0, c->sep_t0 + c->sep_n);
+    return 0;
+}
+
+int lbm_collide(lbm_ctx *c, int64_t step, double time) {
+    (void)time;  // time only enters through the force data
+    if (!c) return fail(LBM_ERR_INVALID, "null context");
+    CU(cudaSetDevice(c->desc.device));
+    int rc = materialize(c);
+    if (rc) return rc;
+    rc = check_force_window(c, step, 1);
+    if (rc) return rc;
+    rc = is64(c) ? do_collide<double>(c, step) : do_collide<float>(c, step);
+    if (rc) return rc;
+    c->have_coll = true;
+    c->resume_ok = false;
+    return 0;
+}
+
+int lbm_stream(lbm_ctx *c) {
+    if (!c) return fail(LBM_ERR_INVALID, "null context");
+    CU(cudaSetDevice(c->desc.device));
+    int rc = materialize(c);
+    if (rc) return rc;
+    if (!c->have_coll) return fail(LBM_ERR_STATE, "stream! needs f_collision: call lbm_collide first");
+    rc = wait_comm(c);
+    if (rc) return rc;
+    if (is64(c)) {
+        KParams<double> p = make_params<double>(c, 1 - c->cur, c->cur);
+        p.nbc = 0;
+        c->ops->stream64(p, c->stream);
+    } else {
+        KParams<float> p = make_params<float>(c, 1 - c->cur, c->cur);
+        p.nbc = 0;
+        c->ops->stream32(p, c->stream);
+    }
+    c->launches += 1;
+    CU(cudaGetLastError());
+    c->resume_ok = false;
+    return 0;
+}
+
+int lbm_apply_bcs(lbm_ctx *c, double time) {
+    (void)time;
+    if (!c) return fail(LBM_ERR_INVALID, "null context");
+    CU(cudaSetDevice(c->desc.device));
+    int rc = materialize(c);
+    if (rc) return rc;
+    if (!c->have_coll) return fail(LBM_ERR_STATE, "apply! needs f_collision: call lbm_collide first");
+    if (c->desc.n_bcs == 0) return 0;
+    if (is64(c)) {
+        KParams<double> p = make_params<double>(c, c->cur, c->cur);
+        p.aux = origin<double>(c, 1 - c->cur);
+        c->ops->bcs64(p, c->stream);
+    } else {
+        KParams<float> p = make_params<float>(c, c->cur, c->cur);
+        p.aux = origin<float>(c, 1 - c->cur);
+        c->ops->bcs32(p, c->stream);
+    }
+    c->launches += 1;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int lbm_step(lbm_ctx *c, int64_t t0, int64_t nsteps, double dt) {
+    (void)dt;  // time = t*dt only enters through the force data (indexed by t)
+    if (!c) return fail(LBM_ERR_INVALID, "null context");
+    if (nsteps < 0) return fail(LBM_ERR_INVALID, "nsteps %lld", (long long)nsteps);
+    if (nsteps == 0) return 0;
+    CU(cudaSetDevice(c->desc.device));
+    int rc = check_force_window(c, t0, nsteps);
+    if (rc) return rc;
+    CU(cudaEventRecord(c->ev_t0, c->stream));
+    rc = is64(c) ? do_steps<double>(c, t0, nsteps) : do_steps<float>(c, t0, nsteps);
+    if (rc) return rc;
+    if (c->desc.world > 1) {
+        rc = wait_comm(c);  // the batch ends when the last halo has landed
+        if (rc) return rc;
+    }
+    CU(cudaEventRecord(c->ev_t1, c->stream));
+    c->timed = true;
+    return 0;
+}
+
+int lbm_sync(lbm_ctx *c) {
+    if (!c) return fail(LBM_ERR_INVALID, "null context");
+    CU(cudaSetDevice(c->desc.device));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->comm_stream));
+    return 0;
+}
+
+int lbm_last_step_ms(lbm_ctx *c, float *ms) {
+    if (!c || !ms) return fail(LBM_ERR_INVALID, "null argument");
+    if (!c->timed) return fail(LBM_ERR_STATE, "no lbm_step batch has run");
+    CU(cudaSetDevice(c->desc.device));
+    CU(cudaEventSynchronize(c->ev_t1));
+    CU(cudaEventElapsedTime(ms, c->ev_t0, c->ev_t1));
+    return 0;
+}
+
+int lbm_timer_start(lbm_ctx *c) {
+    if (!c) return fail(LBM_ERR_INVALID, "null context");
+    CU(cudaSetDevice(c->desc.device));
+    CU(cudaEventRecord(c->ev_u0, c->stream));
+    return 0;
+}
+
+int lbm_timer_stop(lbm_ctx *c, float *ms) {
+    if (!c || !ms) return fail(LBM_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(c->desc.device));
+    CU(cudaEventRecord(c->ev_u1, c->stream));
+    CU(cudaEventSynchronize(c->ev_u1));
+    CU(cudaEventElapsedTime(ms, c->ev_u0, c->ev_u1));
+    return 0;
+}
+
+int64_t lbm_kernel_launches(const lbm_ctx *c) { return c ? c->launches : 0; }
+
+int lbm_set_option(lbm_ctx *c, const char *key, int64_t value) {
+    if (!c || !key) return fail(LBM_ERR_INVALID, "null argument");
+    if (!strcmp(key, "variant")) c->opt_variant = (int)value;
+    else if (!strcmp(key, "overlap")) c->opt_overlap = (int)value;
+    else return fail(LBM_ERR_INVALID, "unknown option '%s'", key);
+    return 0;
+}
+
+int lbm_moments(lbm_ctx *c, double tau_visc, double *rho, double *ux, double *uy, double *p, double *p_track,
+                double *sxx, double *sxy, double *syy) {
+    if (!c) return fail(LBM_ERR_INVALID, "null context");
+    CU(cudaSetDevice(c->desc.device));
+    int rc = wait_comm(c);
+    if (rc) return rc;
+    double *host[8] = {rho, ux, uy, p, p_track, sxx, sxy, syy};
+    double *dev[8] = {nullptr};
+    const size_t N = (size_t)c->nyl * c->desc.nx;
+    for (int k = 0; k < 8; ++k)
+        if (host[k]) {
+            cudaError_t e = cudaMalloc(&dev[k], N * 8);
+            if (e != cudaSuccess) {
+                for (int j = 0; j < k; ++j) if (dev[j]) cudaFree(dev[j]);
+                return fail(LBM_ERR_NOMEM, "cudaMalloc(%zu): %s", N * 8, cudaGetErrorString(e));
+            }
+        }
+    MomentsOut m{dev[0], dev[1], dev[2], dev[3], dev[4], dev[5], dev[6], dev[7], tau_visc};
+    const bool pull = c->state == ST_COLLIDED;
+    if (is64(c)) c->ops->moments64(pull, make_params<double>(c, c->cur, c->cur), m, c->stream);
+    else c->ops->moments32(pull, make_params<float>(c, c->cur, c->cur), m, c->stream);
+    c->launches += 1;
+    cudaError_t e = cudaGetLastError();
+    for (int k = 0; k < 8 && e == cudaSuccess; ++k)
+        if (host[k]) e = cudaMemcpyAsync(host[k], dev[k], N * 8, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    for (int k = 0; k < 8; ++k) if (dev[k]) cudaFree(dev[k]);
+    if (e != cudaSuccess) return fail(LBM_ERR_CUDA, "lbm_moments: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int lbm_reduce(lbm_ctx *c, int32_t kind, double *out, int32_t n) {
+    if (!c || !out || n < 1) return fail(LBM_ERR_INVALID, "bad argument");
+    if (kind < LBM_REDUCE_MEAN_UX || kind > LBM_REDUCE_CONSERVED) return fail(LBM_ERR_INVALID, "reduce kind %d", kind);
+    CU(cudaSetDevice(c->desc.device));
+    int rc = wait_comm(c);
+    if (rc) return rc;
+    const size_t N = (size_t)c->nyl * c->desc.nx;
+    if (kind == LBM_REDUCE_VELOCITY_CHANGE && !c->u_old) {
+        CU(cudaMalloc(&c->u_old, 2 * N * 8));
+        CU(cudaMemsetAsync(c->u_old, 0, 2 * N * 8, c->stream));  // zeros(T, 2) per node, stopping_criteria.jl:64
+    }
+    ReduceArgs ra{kind, c->partials, c->u_old, c->red_out, c->red_blocks};
+    const bool pull = c->state == ST_COLLIDED;
+    if (is64(c)) c->ops->reduce64(pull, make_params<double>(c, c->cur, c->cur), ra, c->stream);
+    else c->ops->reduce32(pull, make_params<float>(c, c->cur, c->cur), ra, c->stream);
+    c->launches += 2;
+    CU(cudaGetLastError());
+    double h[4];
+    CU(cudaMemcpyAsync(h, c->red_out, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < n && k < 4; ++k) out[k] = h[k];
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,300 @@
+"""ctypes binding of liblbm_b200.so (C ABI: include/lbm_b200.h).
+
+This is the exact surface a Julia `ccall` shim binds (see INTEGRATION.md and
+latticeboltzmann.jl_b200/julia/LatticeBoltzmannB200.jl); Python is the host language
+here only because Julia is not installed in the build image.
+
+There is NO CPU fallback: importing works without a GPU (so that the ABI can be
+inspected), but every compute entry point needs the CUDA library and a device, and
+raises `LbmError` otherwise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+LBM_ABI_VERSION = 1
+LBM_MAX_Q = 37
+LBM_MAX_TAU = 16
+LBM_MAX_BCS = 8
+LBM_NCCL_ID_BYTES = 128
+
+# enums (include/lbm_b200.h)
+LATTICE_IDS = {"D2Q4": 0, "D2Q5": 1, "D2Q9": 2, "D2Q13": 3, "D2Q17": 4, "D2Q21": 5, "D2Q37": 6}
+F64, F32 = 0, 1
+SRT, TRT, MRT = 0, 1, 2
+ARITH_EXACT, ARITH_FAST = 0, 1
+BC_BOUNCE_BACK, BC_MOVING_WALL = 0, 1
+NORTH, EAST, SOUTH, WEST = 0, 1, 2, 3
+REDUCE_MEAN_UX, REDUCE_VELOCITY_CHANGE, REDUCE_CONSERVED = 0, 1, 2
+
+EXPORTS = [
+    "lbm_abi_version", "lbm_last_error", "lbm_lattice_info", "lbm_nccl_unique_id", "lbm_create",
+    "lbm_destroy", "lbm_local_rows", "lbm_upload_f", "lbm_upload_f_collision", "lbm_download_f",
+    "lbm_download_f_collision",
+    "lbm_set_force_none", "lbm_set_force_uniform", "lbm_set_force_field", "lbm_set_force_separable",
+    "lbm_collide", "lbm_stream", "lbm_apply_bcs", "lbm_step", "lbm_sync", "lbm_moments", "lbm_reduce",
+    "lbm_kernel_launches", "lbm_last_step_ms", "lbm_timer_start", "lbm_timer_stop", "lbm_set_option",
+]
+
+
+class LbmError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"liblbm_b200 error {code}: {msg}")
+        self.code = code
+
+
+class lbm_bc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("direction", C.c_int32),
+                ("x0", C.c_int32), ("x1", C.c_int32), ("y0", C.c_int32), ("y1", C.c_int32),
+                ("u", C.c_double * 2), ("rho", C.c_double), ("T", C.c_double)]
+
+
+class lbm_desc(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("nx", C.c_int32), ("ny", C.c_int32),
+                ("lattice", C.c_int32), ("dtype", C.c_int32), ("collision", C.c_int32),
+                ("arith", C.c_int32), ("ntau", C.c_int32), ("tau", C.c_double * LBM_MAX_TAU),
+                ("n_bcs", C.c_int32), ("bcs", lbm_bc * LBM_MAX_BCS),
+                ("device", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
+                ("nccl_id", C.c_uint8 * LBM_NCCL_ID_BYTES)]
+
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.environ.get("LBM_B200_LIB", os.path.join(_PKG, "liblbm_b200.so"))
+_lib = None
+
+
+def lib():
+    """Loads liblbm_b200.so; fails loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LbmError(-1, f"{LIB_PATH} not found: build it with `make -C latticeboltzmann.jl_b200/csrc` "
+                           "(or __graft_entry__.build()); there is no CPU fallback")
+    l = C.CDLL(LIB_PATH)
+    dp = C.POINTER(C.c_double)
+    ip = C.POINTER(C.c_int32)
+    vp = C.c_void_p
+    l.lbm_abi_version.restype = C.c_int
+    l.lbm_last_error.restype = C.c_char_p
+    l.lbm_lattice_info.argtypes = [C.c_int32, ip, ip, ip, dp, dp, ip, ip, ip, ip]
+    l.lbm_nccl_unique_id.argtypes = [C.POINTER(C.c_uint8)]
+    l.lbm_create.argtypes = [C.POINTER(lbm_desc), C.POINTER(vp)]
+    l.lbm_destroy.argtypes = [vp]
+    l.lbm_destroy.restype = None
+    l.lbm_local_rows.argtypes = [vp, ip, ip]
+    l.lbm_upload_f.argtypes = [vp, vp]
+    l.lbm_upload_f_collision.argtypes = [vp, vp]
+    l.lbm_download_f.argtypes = [vp, vp]
+    l.lbm_download_f_collision.argtypes = [vp, vp]
+    l.lbm_set_force_none.argtypes = [vp]
+    l.lbm_set_force_uniform.argtypes = [vp, C.c_double, C.c_double]
+    l.lbm_set_force_field.argtypes = [vp, vp]
+    l.lbm_set_force_separable.argtypes = [vp, C.c_int64, C.c_int32, vp, vp]
+    l.lbm_collide.argtypes = [vp, C.c_int64, C.c_double]
+    l.lbm_stream.argtypes = [vp]
+    l.lbm_apply_bcs.argtypes = [vp, C.c_double]
+    l.lbm_step.argtypes = [vp, C.c_int64, C.c_int64, C.c_double]
+    l.lbm_sync.argtypes = [vp]
+    l.lbm_moments.argtypes = [vp, C.c_double] + [vp] * 8
+    l.lbm_reduce.argtypes = [vp, C.c_int32, dp, C.c_int32]
+    l.lbm_kernel_launches.argtypes = [vp]
+    l.lbm_kernel_launches.restype = C.c_int64
+    l.lbm_last_step_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    l.lbm_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
+    l.lbm_timer_start.argtypes = [vp]
+    l.lbm_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
+    if l.lbm_abi_version() != LBM_ABI_VERSION:
+        raise LbmError(-1, f"ABI version mismatch: library {l.lbm_abi_version()} != binding {LBM_ABI_VERSION}")
+    _lib = l
+    return l
+
+
+def check(rc):
+    if rc != 0:
+        raise LbmError(rc, lib().lbm_last_error().decode(errors="replace"))
+
+
+def lattice_info(lattice_id):
+    """Built-in tables of one quadrature (lbm_lattice_info)."""
+    q = C.c_int32()
+    cx = (C.c_int32 * LBM_MAX_Q)()
+    cy = (C.c_int32 * LBM_MAX_Q)()
+    opp = (C.c_int32 * LBM_MAX_Q)()
+    w = (C.c_double * LBM_MAX_Q)()
+    css = C.c_double()
+    eq_order, n, halo = C.c_int32(), C.c_int32(), C.c_int32()
+    check(lib().lbm_lattice_info(lattice_id, C.byref(q), cx, cy, w, C.byref(css), opp, C.byref(eq_order),
+                                 C.byref(n), C.byref(halo)))
+    Q = q.value
+    return dict(Q=Q, cx=np.array(cx[:Q]), cy=np.array(cy[:Q]), w=np.array(w[:Q]), css=css.value,
+                opposite=np.array(opp[:Q]), eq_order=eq_order.value, hermite_order=n.value, halo=halo.value)
+
+
+def nccl_unique_id():
+    buf = (C.c_uint8 * LBM_NCCL_ID_BYTES)()
+    check(lib().lbm_nccl_unique_id(buf))
+    return bytes(buf)
+
+
+def _as_f64(a, shape=None):
+    a = np.asarray(a, dtype=np.float64)
+    if shape is not None and tuple(a.shape) != tuple(shape):
+        raise ValueError(f"expected shape {shape}, got {a.shape}")
+    return a
+
+
+class Context:
+    """One lbm_ctx.  Population arrays are numpy Float64 of shape (NX, NY_local, Q) in Fortran
+    order -- the memory order of Julia's `f[x, y, i]`."""
+
+    def __init__(self, nx, ny, lattice, collision, tau, bcs=(), dtype=F64, arith=ARITH_EXACT, device=0,
+                 rank=0, world=1, nccl_id=None):
+        d = lbm_desc()
+        d.abi_version = LBM_ABI_VERSION
+        d.nx, d.ny = int(nx), int(ny)
+        d.lattice = LATTICE_IDS[lattice] if isinstance(lattice, str) else int(lattice)
+        d.dtype, d.collision, d.arith = int(dtype), int(collision), int(arith)
+        tau = [float(t) for t in np.atleast_1d(tau)]
+        if len(tau) > LBM_MAX_TAU:
+            raise ValueError("too many relaxation times")
+        d.ntau = len(tau)
+        for i, t in enumerate(tau):
+            d.tau[i] = t
+        bcs = list(bcs)
+        if len(bcs) > LBM_MAX_BCS:
+            raise ValueError(f"at most {LBM_MAX_BCS} boundary conditions")
+        d.n_bcs = len(bcs)
+        for i, b in enumerate(bcs):
+            d.bcs[i] = b
+        d.device, d.rank, d.world = int(device), int(rank), int(world)
+        if world > 1:
+            if nccl_id is None or len(nccl_id) != LBM_NCCL_ID_BYTES:
+                raise ValueError("world > 1 needs the 128-byte NCCL id from rank 0")
+            C.memmove(d.nccl_id, nccl_id, LBM_NCCL_ID_BYTES)
+        self._h = C.c_void_p()
+        self.desc = d
+        check(lib().lbm_create(C.byref(d), C.byref(self._h)))
+        y0, nyl = C.c_int32(), C.c_int32()
+        check(lib().lbm_local_rows(self._h, C.byref(y0), C.byref(nyl)))
+        self.nx, self.ny, self.y0, self.ny_local = d.nx, d.ny, y0.value, nyl.value
+        self.Q = lattice_info(d.lattice)["Q"]
+        self.shape = (self.nx, self.ny_local, self.Q)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().lbm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- populations ---------------------------------------------------------------------
+    def _check_f(self, f, writable=False):
+        if not isinstance(f, np.ndarray) or f.dtype != np.float64 or f.shape != self.shape or not f.flags.f_contiguous:
+            raise ValueError(f"populations must be a Fortran-ordered float64 array of shape {self.shape}")
+        if writable and not f.flags.writeable:
+            raise ValueError("read-only array")
+        return f
+
+    def new_f(self):
+        return np.empty(self.shape, dtype=np.float64, order="F")
+
+    def upload_f(self, f):
+        f = np.asfortranarray(f, dtype=np.float64)
+        check(lib().lbm_upload_f(self._h, self._check_f(f).ctypes.data))
+
+    def upload_f_collision(self, f):
+        f = np.asfortranarray(f, dtype=np.float64)
+        check(lib().lbm_upload_f_collision(self._h, self._check_f(f).ctypes.data))
+
+    def download_f(self, out=None):
+        out = self.new_f() if out is None else self._check_f(out, True)
+        check(lib().lbm_download_f(self._h, out.ctypes.data))
+        return out
+
+    def download_f_collision(self, out=None):
+        out = self.new_f() if out is None else self._check_f(out, True)
+        check(lib().lbm_download_f_collision(self._h, out.ctypes.data))
+        return out
+
+    # ---- force ---------------------------------------------------------------------------
+    def set_force_none(self):
+        check(lib().lbm_set_force_none(self._h))
+
+    def set_force_uniform(self, fx, fy):
+        check(lib().lbm_set_force_uniform(self._h, float(fx), float(fy)))
+
+    def set_force_field(self, Fx, Fy):
+        """Fx, Fy: arrays (NX, NY_local)."""
+        F = np.empty((self.nx, self.ny_local, 2), dtype=np.float64, order="F")
+        F[:, :, 0] = _as_f64(Fx, (self.nx, self.ny_local))
+        F[:, :, 1] = _as_f64(Fy, (self.nx, self.ny_local))
+        check(lib().lbm_set_force_field(self._h, F.ctypes.data))
+
+    def set_force_separable(self, t0, fx_of_y, fy_of_x):
+        """fx_of_y: (nsteps, NY_local), fy_of_x: (nsteps, NX), C order."""
+        fx = np.ascontiguousarray(fx_of_y, dtype=np.float64)
+        fy = np.ascontiguousarray(fy_of_x, dtype=np.float64)
+        n = fx.shape[0]
+        if fx.shape != (n, self.ny_local) or fy.shape != (n, self.nx):
+            raise ValueError("separable force tables must be (nsteps, NY_local) and (nsteps, NX)")
+        check(lib().lbm_set_force_separable(self._h, int(t0), n, fx.ctypes.data, fy.ctypes.data))
+
+    # ---- operators -----------------------------------------------------------------------
+    def collide(self, step=0, time=0.0):
+        check(lib().lbm_collide(self._h, int(step), float(time)))
+
+    def stream(self):
+        check(lib().lbm_stream(self._h))
+
+    def apply_bcs(self, time=0.0):
+        check(lib().lbm_apply_bcs(self._h, float(time)))
+
+    def step(self, t0, nsteps, dt=1.0):
+        check(lib().lbm_step(self._h, int(t0), int(nsteps), float(dt)))
+
+    def sync(self):
+        check(lib().lbm_sync(self._h))
+
+    # ---- diagnostics ---------------------------------------------------------------------
+    FIELDS = ("rho", "ux", "uy", "p", "p_track", "sxx", "sxy", "syy")
+
+    def moments(self, tau_visc=1.0, fields=("rho", "ux", "uy")):
+        """dict of (NX, NY_local) Fortran arrays for the requested fields (lbm_moments)."""
+        out = {k: np.empty((self.nx, self.ny_local), dtype=np.float64, order="F") for k in fields}
+        ptrs = [out[k].ctypes.data if k in out else None for k in self.FIELDS]
+        check(lib().lbm_moments(self._h, float(tau_visc), *ptrs))
+        return out
+
+    def reduce(self, kind):
+        buf = (C.c_double * 4)()
+        check(lib().lbm_reduce(self._h, int(kind), buf, 4))
+        return np.array(buf[:])
+
+    # ---- introspection -------------------------------------------------------------------
+    @property
+    def kernel_launches(self):
+        return int(lib().lbm_kernel_launches(self._h))
+
+    def last_step_ms(self):
+        ms = C.c_float()
+        check(lib().lbm_last_step_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def timer_start(self):
+        check(lib().lbm_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        check(lib().lbm_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    def set_option(self, key, value):
+        check(lib().lbm_set_option(self._h, key.encode(), int(value)))

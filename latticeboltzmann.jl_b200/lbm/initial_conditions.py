@@ -1,0 +1,114 @@
+"""Initialisation strategies of the Julia API (src/initial_conditions{.jl,/*.jl}), host side.
+
+`initialize(strategy, q, problem, cm)` returns `f` of shape (NX, NY, Q), Fortran order, Float64
+(== Julia's `Array{Float64,3}(NX, NY, Q)` in memory).  `rows=(y0, ny)` builds only a y-slab.
+"""
+import numpy as np
+
+from . import vdf
+from .problems import TGV
+
+
+class InitializationStrategy:
+    pass
+
+
+class AnalyticalEquilibrium(InitializationStrategy):
+    """analytical_equilibrium.jl:8-17."""
+
+
+class ConstantDensity(InitializationStrategy):
+    """constant_density.jl:8-20."""
+
+
+class AnalyticalVelocityAndStress(InitializationStrategy):
+    """analytical_velocity_stress.jl:4-31."""
+
+
+class AnalyticalEquilibriumAndOffEquilibrium(InitializationStrategy):
+    """analytical_offequilibrium.jl:9-87."""
+
+
+class ZeroVelocityInitialCondition(InitializationStrategy):
+    """initial_conditions.jl:37-53."""
+
+
+class AnalyticalVelocity(InitializationStrategy):
+    """analytical_velocity.jl -- broken in the reference (calls an undefined
+    pressure(problem, x, y), :21,39); kept so that the name resolves."""
+
+
+class IterativeInitializationMeiEtAl(InitializationStrategy):
+    """mei_et_al.jl -- out of scope."""
+
+    def __init__(self, tau=1.0, eps=1e-7):
+        self.tau, self.eps = tau, eps
+
+
+def default_strategy(problem):
+    """InitializationStrategy(problem) (initial_conditions.jl:5)."""
+    return AnalyticalEquilibrium()
+
+
+def _stack_u(ux, uy):
+    return np.stack([ux, uy], axis=-1)
+
+
+def _equilibrium_problem(q, problem, X, Y):
+    # equilibrium(q, problem, x, y): problems.jl:121-128
+    rho = problem.lattice_density(q, X, Y)
+    ux, uy = problem.lattice_velocity(q, X, Y)
+    T = problem.lattice_temperature(q, X, Y)
+    return vdf.hermite_based_equilibrium(q, rho, _stack_u(ux, uy), T)
+
+
+def _dot_H2_sym_grad(q, grad):
+    """dot(hermite(Val{2}, c_i, q), grad + grad') for every population -> (..., Q)."""
+    (a11, a12), (a21, a22) = grad
+    S = np.stack([np.stack([a11 + a11, a12 + a21], -1), np.stack([a21 + a12, a22 + a22], -1)], -2)
+    out = np.empty(S.shape[:-2] + (q.Q,))
+    for i in range(q.Q):
+        H = vdf.hermite(2, (int(q.abscissae[0, i]), int(q.abscissae[1, i])), q)
+        out[..., i] = np.tensordot(S, H, axes=([-2, -1], [0, 1]))
+    return out
+
+
+def initialize(strategy, q, problem, cm=None, rows=None):
+    """initialize(strategy, q, problem, cm = SRT) (initial_conditions.jl:7-22)."""
+    y0, ny = (0, problem.NY) if rows is None else rows
+    X, Y = problem.grid(y0, ny)
+    one = np.ones_like(X)
+    cs = q.speed_of_sound_squared
+    if isinstance(strategy, ZeroVelocityInitialCondition):
+        f = one[..., None] * q.weights
+    elif isinstance(strategy, AnalyticalEquilibrium):
+        f = _equilibrium_problem(q, problem, X, Y)
+    elif isinstance(strategy, ConstantDensity):
+        ux, uy = problem.lattice_velocity(q, X, Y)
+        f = vdf.hermite_based_equilibrium(q, one, _stack_u(ux, uy), 1.0)
+    elif isinstance(strategy, AnalyticalVelocityAndStress):
+        ux, uy = problem.lattice_velocity(q, X, Y)
+        f = vdf.hermite_based_equilibrium(q, one, _stack_u(ux, uy), 1.0)
+        g = problem.velocity_gradient(X, Y, 0.0)
+        g = tuple(tuple(problem.u_max ** 2 * c for c in row) for row in g)
+        tau_eff = cs * problem.lattice_viscosity() + 0.5
+        f = f - q.weights * (cs * tau_eff * 1.0 * 1.0) / 2 * _dot_H2_sym_grad(q, g)
+    elif isinstance(strategy, AnalyticalEquilibriumAndOffEquilibrium):
+        f = _equilibrium_problem(q, problem, X, Y)
+        tau = cs * problem.lattice_viscosity()
+        if isinstance(problem, TGV):  # analytical_offequilibrium.jl:50-87
+            rho = problem.lattice_density(q, X, Y)
+            g = problem.velocity_gradient(X, Y, 0.0)
+            f = f - q.weights * (cs * (tau + 0.5) * rho[..., None] * 1.0) / 2 * _dot_H2_sym_grad(q, g)
+        else:  # :10-49
+            g = problem.velocity_gradient(X, Y, 0.0)
+            g = tuple(tuple(problem.u_max ** 2 * c for c in row) for row in g)
+            factor = problem.domain_size[0] * problem.domain_size[1]
+            f = f + (-factor * q.weights * 0.5 * ((tau + 0.5) * cs)) * _dot_H2_sym_grad(q, g)
+    elif isinstance(strategy, AnalyticalVelocity):
+        raise NotImplementedError("AnalyticalVelocity is broken in the reference (analytical_velocity.jl:21,39)")
+    elif isinstance(strategy, IterativeInitializationMeiEtAl):
+        raise NotImplementedError("Mei et al. initialisation is out of scope (SURVEY.md section 8f)")
+    else:
+        raise TypeError(f"unknown initialisation strategy {strategy!r}")
+    return np.asfortranarray(f, dtype=np.float64)

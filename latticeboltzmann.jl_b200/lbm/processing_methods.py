@@ -1,0 +1,250 @@
+"""Processing methods and stop criteria of the Julia API (src/processing_methods{.jl,/*}).
+
+`next_(pm, q, f_in, t)` mirrors `next!(pm, q, f_in, t)::Bool`; `f_in` is the device-resident
+state (`DeviceState`, what `simulate` passes) or a host array (uploaded to a scratch context).
+Per-node moments and grid reductions run in the CUDA library (`lbm_moments`, `lbm_reduce`);
+the host only combines them with the problem's analytic fields.  Plotting is out of scope.
+"""
+import math
+import warnings
+
+import numpy as np
+
+from . import _abi
+from .problems import (CouetteFlow, DecayingShearFlow, LidDrivenCavityFlow, PoiseuilleFlow, TGV,
+                       TaylorGreenVortex)
+
+
+# ---------------------------------------------------------------------------------------------
+# stop criteria (processing_methods/stopping_criteria/stopping_criteria.jl)
+# ---------------------------------------------------------------------------------------------
+class StopCriteriaBase:
+    active = True
+
+    def should_stop_(self, q, state):
+        return False
+
+
+class NoStoppingCriteria(StopCriteriaBase):
+    active = False
+
+
+class MeanVelocityStoppingCriteria(StopCriteriaBase):
+    """:3-55."""
+
+    def __init__(self, old_mean_velocity, tolerance, problem):
+        self.old_mean_velocity = old_mean_velocity
+        self.tolerance = tolerance
+        self.problem = problem
+
+    def should_stop_(self, q, state):
+        s = state.reduce(_abi.REDUCE_MEAN_UX)
+        u_mean = np.float64(s[0]) / np.float64(s[1])
+        with np.errstate(divide="ignore", invalid="ignore"):
+            converged = abs(u_mean / np.float64(self.old_mean_velocity) - 1)
+        if converged < self.tolerance:
+            return True
+        if math.isnan(u_mean):
+            warnings.warn("nan in velocity profile")
+            return True
+        self.old_mean_velocity = float(u_mean)
+        return False
+
+
+class VelocityConvergenceStoppingCriteria(StopCriteriaBase):
+    """:57-115; the previous velocity field lives on the device."""
+
+    def __init__(self, tolerance, problem):
+        self.tolerance = tolerance
+        self.problem = problem
+
+    def should_stop_(self, q, state):
+        s = state.reduce(_abi.REDUCE_VELOCITY_CHANGE)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            converged = np.sqrt(np.float64(s[0])) / np.float64(s[1])  # denominator not sqrt'ed (:101)
+        if converged < self.tolerance:
+            return True
+        if math.isnan(converged):
+            warnings.warn("nan in velocity profile")
+            return True
+        return False
+
+
+def StopCriteria(problem):
+    """:8-15."""
+    if isinstance(problem, PoiseuilleFlow):
+        return MeanVelocityStoppingCriteria(0.0, 1e-12, problem)
+    if isinstance(problem, CouetteFlow):
+        return MeanVelocityStoppingCriteria(0.0, 1e-7, problem)
+    if isinstance(problem, LidDrivenCavityFlow):
+        return MeanVelocityStoppingCriteria(0.0, 1e-5, problem)
+    if isinstance(problem, DecayingShearFlow) and problem.static:
+        return MeanVelocityStoppingCriteria(0.0, 1e-8, problem)
+    return NoStoppingCriteria()
+
+
+def should_stop_(sc, q, state):
+    return sc.should_stop_(q, state)
+
+
+# ---------------------------------------------------------------------------------------------
+# processing methods
+# ---------------------------------------------------------------------------------------------
+class ProcessingMethodBase:
+    problem = None
+
+    def noop(self, t):
+        """True when next_(pm, q, f, t) neither reads f nor has side effects -- lets `simulate`
+        keep the device running without a host round trip."""
+        return False
+
+
+def _sdiv(a, b):
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.sqrt(np.float64(a) / np.float64(b))
+
+
+class TrackHydrodynamicErrors(ProcessingMethodBase):
+    """track_hydrodynamic_errors.jl (visualisation omitted).  df rows are dicts with the
+    reference's field names (σ spelled `s`: error_σ_xx -> error_sxx ...)."""
+
+    def __init__(self, problem, should_process, n_steps, stop_criteria=None):
+        self.problem = problem
+        self.should_process = should_process
+        self.n_steps = n_steps
+        self.stop_criteria = StopCriteria(problem) if stop_criteria is None else stop_criteria
+        self.df = []
+
+    def noop(self, t):
+        if t % 100 == 0 and self.stop_criteria.active:
+            return False
+        return (not self.should_process) and t != self.n_steps
+
+    def next_(self, q, state, t):
+        should_stop = False
+        if t % 100 == 0:
+            if self.stop_criteria.should_stop_(q, state):
+                should_stop = True
+        if (not should_stop) and t != self.n_steps:
+            if not self.should_process:
+                return False
+        pr = self.problem
+        nx, ny = pr.NX, pr.NY
+        xstep, ystep = pr.range_steps()
+        time = t * pr.delta_t()
+        Delta = ystep * xstep
+        if nx == 1:
+            Delta = ystep
+            if ny == 1:
+                Delta = 1.0
+        elif ny == 1:
+            Delta = xstep
+        tau = q.speed_of_sound_squared * pr.lattice_viscosity()
+        h = state.moments(tau, ("rho", "ux", "uy", "p_track", "sxx", "sxy", "syy"))
+        X, Y = pr.grid(state.y0, state.ny_local)
+        e_rho = pr.density(q, X, Y, time)
+        e_ux, e_uy = pr.velocity(X, Y, time)
+        e_p = pr.pressure(q, X, Y, time)
+        (e_sxx, e_sxy), (e_syx, e_syy) = pr.deviatoric_tensor(q, X, Y, time)
+        rho = h["rho"]
+        ux, uy = h["ux"] / pr.u_max, h["uy"] / pr.u_max
+        fac = 1 / pr.u_max ** 2
+        sxx, sxy, syy = h["sxx"] * fac, h["sxy"] * fac, h["syy"] * fac
+        sums = np.array([
+            np.sum((rho - e_rho) ** 2), np.sum((ux - e_ux) ** 2 + (uy - e_uy) ** 2), np.sum(e_ux ** 2 + e_uy ** 2),
+            np.sum((h["p_track"] - e_p) ** 2), np.sum(e_p ** 2),
+            np.sum((e_sxx - sxx) ** 2), np.sum(e_sxx ** 2), np.sum((e_sxy - sxy) ** 2), np.sum(e_sxy ** 2),
+            np.sum((e_syy - syy) ** 2), np.sum(e_syy ** 2), np.sum((e_syx - sxy) ** 2), np.sum(e_syx ** 2),
+            np.sum(rho), np.sum(rho * (ux + uy)), np.sum(rho * (ux ** 2 + uy ** 2))])
+        s = state.allreduce(sums)
+        self.df.append(dict(
+            timestep=t, error_rho=float(np.sqrt(s[0])), error_u=float(_sdiv(s[1], s[2])),
+            error_p=float(_sdiv(s[3], s[4])), error_sxx=float(_sdiv(s[5], s[6])), error_sxy=float(_sdiv(s[7], s[8])),
+            error_syy=float(_sdiv(s[9], s[10])), error_syx=float(_sdiv(s[11], s[12])),
+            mass=Delta * s[13], momentum=Delta * s[14], energy=Delta * s[15]))
+        return should_stop
+
+
+class CompareWithAnalyticalSolution(ProcessingMethodBase):
+    """processing_methods.jl:31-269 (visualisation omitted)."""
+
+    def __init__(self, problem, should_process, n_steps, stop_criteria=None):
+        self.problem = problem
+        self.should_process = should_process
+        self.n_steps = n_steps
+        self.stop_criteria = StopCriteria(problem) if stop_criteria is None else stop_criteria
+        self.df = []
+
+    def noop(self, t):
+        if t % 100 == 0 and self.stop_criteria.active:
+            return False
+        return (not self.should_process) and t != self.n_steps
+
+    def next_(self, q, state, t):
+        pr = self.problem
+        if t % 100 == 0:
+            if self.stop_criteria.should_stop_(q, state):
+                process_(pr, q, state, t * pr.delta_t(), self.df)
+                return True
+        if not self.should_process:
+            if t != self.n_steps:
+                return False
+        process_(pr, q, state, t * pr.delta_t(), self.df)
+        return False
+
+
+def process_(problem, q, state, time, stats, should_visualize=False):
+    """process!(problem, q, f_in, time, stats) (processing_methods.jl:142-269)."""
+    pr = problem
+    xstep, ystep = pr.range_steps()
+    h = state.moments(1.0, ("rho", "ux", "uy", "p"))
+    rho, p = h["rho"], h["p"]
+    T = p / rho
+    ux, uy = h["ux"] / pr.u_max, h["uy"] / pr.u_max
+    kin = (ux ** 2 + uy ** 2) * rho
+    X, Y = pr.grid(state.y0, state.ny_local)
+    e_rho = pr.density(q, X, Y, time)
+    e_p = pr.pressure(q, X, Y, time)
+    e_ux, e_uy = pr.velocity(X, Y, time)
+    e_T = e_p / e_rho
+    e_kin = e_ux ** 2 + e_uy ** 2
+    opp = ystep * xstep
+    s = state.allreduce(np.array([
+        np.sum(rho), np.sum((ux + uy) * rho), np.sum(kin + T), np.sum(kin), np.sum(T),
+        np.sum(e_rho), np.sum(e_rho * (e_ux + e_uy)), np.sum(e_kin + e_T), np.sum(e_kin), np.sum(e_T),
+        np.sum(opp * ((ux - e_ux) ** 2 + (uy - e_uy) ** 2)), np.sum(opp * (p - e_p) ** 2)]))
+    stats.append(dict(
+        density=s[0], momentum=s[1], total_energy=s[2], kinetic_energy=s[3], internal_energy=s[4],
+        density_a=s[5], momentum_a=s[6], total_energy_a=s[7], kinetic_energy_a=s[8], internal_energy_a=s[9],
+        error_u=float(np.sqrt(s[10])), error_p=float(np.sqrt(s[11])),
+        error_sxx=0.0, error_sxy=0.0, error_syy=0.0, error_syx=0.0))
+    return False
+
+
+class TakeSnapshots(ProcessingMethodBase):
+    """take_snapshots.jl:3-29: snapshot = copy(f_in) -> a device-to-host download."""
+
+    def __init__(self, problem, every_t):
+        self.problem = problem
+        self.every_t = every_t
+        self.snapshots = []
+        self.timesteps = []
+
+    def noop(self, t):
+        if isinstance(self.every_t, int):
+            return t % self.every_t != 0
+        return t not in self.every_t
+
+    def next_(self, q, state, t):
+        if self.noop(t):
+            return False
+        self.snapshots.append(state.download_f())
+        self.timesteps.append(t)
+        return False
+
+
+def ProcessingMethod(problem, should_process, n_steps, stop_criteria=None):
+    """processing_methods.jl:10-29."""
+    if isinstance(problem, (TaylorGreenVortex, DecayingShearFlow, TGV)):
+        return TrackHydrodynamicErrors(problem, should_process, n_steps, stop_criteria)
+    return CompareWithAnalyticalSolution(problem, should_process, n_steps, stop_criteria)
