@@ -1,0 +1,264 @@
+"""Host-side logic that runs without a GPU: problems / initial conditions of the host mirror
+against the oracle's independent restatement, collision-model factories, the batching of
+`simulate`, and the y-slab decomposition (world_size 2, gloo)."""
+import os
+
+import numpy as np
+import pytest
+
+import lbm
+import oracle.lbm_oracle as O
+from conftest import to_oracle_layout
+
+PAIRS = [
+    ("TGV", lambda q: lbm.TGV(q, 0.8, 1, 8, 12), lambda q: O.TGV(q, 0.8, 1, 8, 12)),
+    ("TaylorGreenVortex", lambda q: lbm.TaylorGreenVortex(1 / 6, 1, 8, 8), lambda q: O.TaylorGreenVortex(1 / 6, 1, 8, 8)),
+    ("TaylorGreenVortexDecay", lambda q: lbm.TaylorGreenVortex(1 / 6, 1, 8, 8, static=False),
+     lambda q: O.TaylorGreenVortex(1 / 6, 1, 8, 8, static=False)),
+    ("DecayingShearFlow", lambda q: lbm.DecayingShearFlow(1 / 6, 2), lambda q: O.DecayingShearFlow(1 / 6, 2)),
+    ("DecayingShearFlowDecay", lambda q: lbm.DecayingShearFlow(1 / 6, 2, static=False, k_y=1.0),
+     lambda q: O.DecayingShearFlow(1 / 6, 2, static=False, k_y=1.0)),
+    ("PoiseuilleFlow", lambda q: lbm.PoiseuilleFlow(1 / 6, 2), lambda q: O.PoiseuilleFlow(1 / 6, 2)),
+    ("CouetteFlow", lambda q: lbm.CouetteFlow(1 / 6, 2), lambda q: O.CouetteFlow(1 / 6, 2)),
+    ("LidDrivenCavityFlow", lambda q: lbm.LidDrivenCavityFlow(1 / 6, 1), lambda q: O.LidDrivenCavityFlow(1 / 6, 1)),
+]
+
+
+@pytest.mark.parametrize("name,mk_h,mk_o", PAIRS, ids=[p[0] for p in PAIRS])
+def test_problem_fields_match_oracle(name, mk_h, mk_o):
+    q, qo = lbm.D2Q9(), O.L.D2Q9()
+    ph, po = mk_h(q), mk_o(qo)
+    assert (ph.NX, ph.NY, ph.u_max, ph.nu) == (po.NX, po.NY, po.u_max, po.nu)
+    assert ph.delta_x() == po.delta_x() and ph.delta_t() == po.delta_t() and ph.viscosity() == po.viscosity()
+    X, Y = ph.grid()
+    Xo, Yo = po.grid()
+    assert np.array_equal(X.T, Xo) and np.array_equal(Y.T, Yo)
+    for t in (0.0, 0.37):
+        assert np.allclose(ph.density(q, X, Y, t).T, po.density(qo, Xo, Yo, t), rtol=1e-15)
+        assert np.allclose(ph.pressure(q, X, Y, t).T, po.pressure(qo, Xo, Yo, t), rtol=1e-15)
+        for a, b in zip(ph.velocity(X, Y, t), po.velocity(Xo, Yo, t)):
+            assert np.allclose(np.asarray(a).T, b, rtol=1e-15, atol=1e-18)
+        (s11, s12), (s21, s22) = ph.deviatoric_tensor(q, X, Y, t)
+        so = po.deviatoric(qo, Xo, Yo, t)
+        for a, b in ((s11, so[0, 0]), (s12, so[0, 1]), (s21, so[1, 0]), (s22, so[1, 1])):
+            assert np.allclose(np.asarray(a).T, b, rtol=1e-15, atol=1e-18)
+    assert ph.has_external_force() == po.has_external_force()
+    assert len(ph.boundary_conditions()) == len(po.boundary_conditions())
+
+
+@pytest.mark.parametrize("lattice", ["D2Q4", "D2Q9", "D2Q17", "D2Q37"])
+@pytest.mark.parametrize("strategy", ["ZeroVelocityInitialCondition", "AnalyticalEquilibrium", "ConstantDensity",
+                                      "AnalyticalVelocityAndStress", "AnalyticalEquilibriumAndOffEquilibrium"])
+def test_initialize_matches_oracle(lattice, strategy):
+    q, qo = getattr(lbm.Quadratures, lattice), O.L.BY_NAME[lattice]()
+    for mk_h, mk_o in ((PAIRS[0][1], PAIRS[0][2]), (PAIRS[2][1], PAIRS[2][2]), (PAIRS[4][1], PAIRS[4][2])):
+        ph, po = mk_h(q), mk_o(qo)
+        fh = lbm.initialize(getattr(lbm, strategy)(), q, ph)
+        fo = O.initialize(strategy, qo, po)
+        assert fh.shape == (ph.NX, ph.NY, q.Q) and fh.flags.f_contiguous
+        assert np.allclose(to_oracle_layout(fh), fo, rtol=1e-13, atol=1e-17)
+        # slab initialisation == rows of the global one
+        part = lbm.initialize(getattr(lbm, strategy)(), q, ph, rows=(3, 4))
+        assert np.array_equal(part, fh[:, 3:7, :])
+
+
+def test_forces_match_oracle():
+    q, qo = lbm.D2Q9(), O.L.D2Q9()
+    ph, po = lbm.PoiseuilleFlow(1 / 6, 2), O.PoiseuilleFlow(1 / 6, 2)
+    assert np.allclose(lbm.LatticeForce(ph).uniform(), O._problem_force(po), rtol=1e-15)
+    assert np.allclose(lbm.lattice_force(ph, 2, 3, 0.0), O._problem_force(po), rtol=1e-15)
+    ph, po = lbm.TaylorGreenVortex(1 / 6, 1, 8, 8), O.TaylorGreenVortex(1 / 6, 1, 8, 8)
+    Fx, Fy = lbm.LatticeForce(ph).field(0.0, 0, 8)
+    Fo = O._problem_force(po)
+    assert np.allclose(Fx.T, Fo[0], rtol=1e-15) and np.allclose(Fy.T, Fo[1], rtol=1e-15)
+    assert np.allclose(lbm.lattice_force(ph, 2, 5, 0.0), [Fo[0][4, 1], Fo[1][4, 1]], rtol=1e-15)
+    ph, po = lbm.DecayingShearFlow(1 / 6, 2), O.DecayingShearFlow(1 / 6, 2)
+    fx, fy = lbm.LatticeForce(ph).separable(3, 4, 0, ph.NY)
+    for k in range(4):
+        Fo = O._problem_force(po)((3 + k) * po.delta_t())
+        assert np.allclose(fx[k][:, None] + 0 * Fo[0], Fo[0], rtol=1e-15, atol=1e-20)
+        assert np.allclose(fy[k][None, :] + 0 * Fo[1], Fo[1], rtol=1e-15, atol=1e-20)
+    assert lbm.LatticeForce(ph).kind() == "separable"
+
+
+def test_collision_model_factories():
+    q = lbm.D2Q9()
+    pr = lbm.PoiseuilleFlow(1 / 6, 2)
+    srt = lbm.CollisionModel(lbm.SRT, q, pr)
+    assert srt.tau == 3.0 * (1 / 6) + 0.5 and isinstance(srt.force, lbm.LatticeForce)
+    trt = lbm.CollisionModel(lbm.TRT, q, pr)
+    assert trt.tau_symmetric == srt.tau and trt.tau_asymmetric == 0.5 + 0.25 / (srt.tau - 0.5)
+    trt = lbm.CollisionModel(lbm.TRT_Lambda(3 / 16), q, pr)
+    assert trt.tau_asymmetric == 0.5 + (3 / 16) / (srt.tau - 0.5)
+    mrt = lbm.CollisionModel(lbm.MRT, q, pr)
+    assert mrt.taus() == [srt.tau] * 5 and mrt.force is not None  # fill(tau, order(q)), mrt.jl:38
+    inst = lbm.SRT(0.7)
+    assert lbm.CollisionModel(inst, q, pr) is inst and inst.force is None  # instance => no force
+    t2 = lbm.TRT(0.9, 0.6)  # 2-arg convenience ctor is TRT(tau_a, tau_s): trt.jl:6
+    assert (t2.tau_symmetric, t2.tau_asymmetric) == (0.6, 0.9)
+    t3 = lbm.TRT(0.6, 0.9, None)
+    assert (t3.tau_symmetric, t3.tau_asymmetric) == (0.6, 0.9)
+    assert lbm.MRT(lbm.D2Q37(), 0.8).taus() == [0.8] * 4
+    assert lbm.MRT(lbm.D2Q17(), 0.8, 0.9).taus() == [0.8, 0.9, 0.8]
+    assert lbm.MRT(q, 0.8, lambda x, y, t: [1, 1]).force is None  # scalar form drops the force (mrt.jl:19-22)
+    assert lbm.MRT(q, [0.8, 0.9], "F").force == "F"
+    default = lbm.CollisionModel(lbm.collision_models.CollisionModelBase, q, pr)
+    assert isinstance(default, lbm.SRT)
+
+
+class FakeCtx:
+    def __init__(self):
+        self.log = []
+
+    def set_force_none(self):
+        self.log.append(("force_none",))
+
+    def step(self, t0, n, dt):
+        self.log.append(("step", t0, n))
+
+
+class FakeModel(lbm.LatticeBoltzmannModel):
+    def __init__(self, pm):
+        self.ctx = FakeCtx()
+        self.quadrature = lbm.D2Q9()
+        self.collision_model = lbm.SRT(1.0)
+        self.processing_method = pm
+        self.state = lbm.DeviceState.__new__(lbm.DeviceState)
+        self.state.ctx, self.state.cm, self.state.comm = self.ctx, self.collision_model, None
+        self.state._force_window, self.state._static_force_set = None, False
+
+
+class RecordingPM(lbm.processing_methods.ProcessingMethodBase):
+    def __init__(self, every, stop_at=None):
+        self.every, self.stop_at, self.calls = every, stop_at, []
+        self.problem = lbm.TGV(lbm.D2Q9(), 0.8, 1)
+
+    def noop(self, t):
+        return t % self.every != 0
+
+    def next_(self, q, state, t):
+        self.calls.append(t)
+        return t == self.stop_at
+
+
+def test_simulate_batches_steps_between_host_visible_points():
+    # reference loop: for t in time: step(t); if next!(t+1) return; end; next!(last+1)
+    m = FakeModel(RecordingPM(100))
+    lbm.simulate(m, range(0, 251))
+    assert [e for e in m.ctx.log if e[0] == "step"] == [("step", 0, 100), ("step", 100, 100), ("step", 200, 51)]
+    assert m.processing_method.calls == [100, 200, 251]
+    m = FakeModel(RecordingPM(100, stop_at=200))
+    lbm.simulate(m, range(0, 1000))
+    assert [e for e in m.ctx.log if e[0] == "step"] == [("step", 0, 100), ("step", 100, 100)]
+    assert m.processing_method.calls == [100, 200]  # early return: no trailing next!
+    m = FakeModel(RecordingPM(1))
+    lbm.simulate(m, range(1, 4))  # simulate(model, 1:3): next!(2), next!(3), next!(4), trailing next!(4)
+    assert [e for e in m.ctx.log if e[0] == "step"] == [("step", 1, 1), ("step", 2, 1), ("step", 3, 1)]
+    assert m.processing_method.calls == [2, 3, 4, 4]
+    m = FakeModel(None)
+    lbm.simulate(m, range(0, 11))
+    assert [e for e in m.ctx.log if e[0] == "step"] == [("step", 0, 11)]
+
+
+def test_processing_method_noop_matches_next_semantics():
+    pr = lbm.PoiseuilleFlow(1 / 6, 1)
+    pm = lbm.TrackHydrodynamicErrors(pr, False, 5000, lbm.VelocityConvergenceStoppingCriteria(1e-7, pr))
+    assert [t for t in range(1, 301) if not pm.noop(t)] == [100, 200, 300]
+    assert not pm.noop(5000)
+    pm = lbm.TrackHydrodynamicErrors(lbm.TGV(lbm.D2Q9(), 0.8, 1), False, 250)
+    assert [t for t in range(1, 301) if not pm.noop(t)] == [250]  # NoStoppingCriteria: only t == n_steps
+    pm = lbm.TrackHydrodynamicErrors(pr, True, 10)
+    assert not any(pm.noop(t) for t in range(1, 5))
+    snap = lbm.TakeSnapshots(pr, [3, 7])
+    assert [t for t in range(1, 10) if not snap.noop(t)] == [3, 7]
+    assert isinstance(lbm.ProcessingMethod(pr, False, 10), lbm.CompareWithAnalyticalSolution)
+    assert isinstance(lbm.ProcessingMethod(lbm.TGV(lbm.D2Q9(), 0.8, 1), False, 10), lbm.TrackHydrodynamicErrors)
+    assert isinstance(lbm.StopCriteria(pr), lbm.MeanVelocityStoppingCriteria) and lbm.StopCriteria(pr).tolerance == 1e-12
+    assert isinstance(lbm.StopCriteria(lbm.TGV(lbm.D2Q9(), 0.8, 1)), lbm.NoStoppingCriteria)
+
+
+def test_slab_rows_partition():
+    for ny in (1, 7, 64, 4097):
+        for world in (1, 2, 3, 8):
+            rows = [lbm.slab_rows(ny, r, world) for r in range(world)]
+            assert rows[0][0] == 0 and sum(n for _, n in rows) == ny
+            for (a, n), (b, _) in zip(rows, rows[1:]):
+                assert a + n == b
+            assert max(n for _, n in rows) - min(n for _, n in rows) <= 1
+    assert [lbm.halo_rows_per_direction(q) for q in lbm.Quadratures] == [1, 1, 3, 5, 10, 18, 26]
+
+
+# ---- world_size 2 over gloo: the decomposition the CUDA library implements ---------------------
+def _slab_worker(rank, world, port, lattice, ny, nx, nsteps, with_walls, out):
+    import torch.distributed as dist
+    import torch
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    comm = lbm.SlabComm()
+    qo = O.L.BY_NAME[lattice]()
+    q = getattr(lbm.Quadratures, lattice)
+    H = qo.h
+    y0, nyl = lbm.slab_rows(ny, rank, world)
+    rng = np.random.default_rng(99)
+    f_global = np.stack([qo.w[i] * (1 + 0.01 * rng.uniform(-1, 1, (ny, nx))) for i in range(qo.Q)])
+    f = f_global[:, y0:y0 + nyl].copy()
+    cm = O.TRT(0.8, 1.1, (1e-6, 2e-6))
+    bcs = [O.BounceBack("S", (1, nx), (1, ny)), O.MovingWall("N", (1, nx), (1, ny), [0.01, 0.0])] if with_walls else []
+    up, down = (rank + 1) % world, (rank - 1) % world
+    for _ in range(nsteps):
+        fc = O.collide(cm, qo, f)
+        ext = np.zeros((qo.Q, nyl + 2 * H, nx))
+        ext[:, H:H + nyl] = fc
+        # the same messages liblbm_b200 posts: rows of populations moving up go to `up`, ...
+        send_up = torch.from_numpy(np.ascontiguousarray(fc[:, nyl - H:]))
+        send_dn = torch.from_numpy(np.ascontiguousarray(fc[:, :H]))
+        recv_dn, recv_up = torch.empty_like(send_up), torch.empty_like(send_dn)
+        reqs = [dist.isend(send_up, up), dist.isend(send_dn, down), dist.irecv(recv_dn, down), dist.irecv(recv_up, up)]
+        if world == 2:  # both neighbours are the same rank: receives match sends in posting order
+            pass
+        for r in reqs:
+            r.wait()
+        ext[:, :H] = recv_dn.numpy()
+        ext[:, H + nyl:] = recv_up.numpy()
+        fs = np.empty_like(fc)
+        for i in range(qo.Q):
+            cy, cx = int(qo.cy[i]), int(qo.cx[i])
+            fs[i] = np.roll(ext[i, H - cy:H - cy + nyl], cx, axis=1)
+        if bcs:  # BCs are node-local: apply them on the slab embedded at its global rows
+            full_new = np.zeros((qo.Q, ny, nx))
+            full_old = np.zeros((qo.Q, ny, nx))
+            full_new[:, y0:y0 + nyl], full_old[:, y0:y0 + nyl] = fs, fc
+            O.apply_bcs(bcs, qo, full_new, full_old)
+            fs = full_new[:, y0:y0 + nyl]
+        f = fs
+    # distributed diagnostics: per-rank partial sums added by the host (lbm_reduce contract)
+    rho = O.density(qo, [f[i] for i in range(qo.Q)])
+    total = comm.allreduce_sum([rho.sum(), float(rho.size)])
+    out.put((rank, y0, f, total))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("lattice,with_walls", [("D2Q9", False), ("D2Q9", True), ("D2Q37", False), ("D2Q13", True)])
+def test_slab_decomposition_world2_gloo(lattice, with_walls):
+    import torch.multiprocessing as mp
+    ny, nx, nsteps, world = 13, 6, 4, 2
+    qo = O.L.BY_NAME[lattice]()
+    rng = np.random.default_rng(99)
+    f = np.stack([qo.w[i] * (1 + 0.01 * rng.uniform(-1, 1, (ny, nx))) for i in range(qo.Q)])
+    cm = O.TRT(0.8, 1.1, (1e-6, 2e-6))
+    bcs = [O.BounceBack("S", (1, nx), (1, ny)), O.MovingWall("N", (1, nx), (1, ny), [0.01, 0.0])] if with_walls else []
+    for _ in range(nsteps):
+        f, _ = O.step(cm, qo, bcs, f)
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_slab_worker, args=(r, world, port, lattice, ny, nx, nsteps, with_walls, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [out.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, y0, slab, total in results:
+        assert np.array_equal(slab, f[:, y0:y0 + slab.shape[1]]), f"rank {rank} slab differs from the single-domain run"
+        assert total[1] == ny * nx and np.isclose(total[0], O.density(qo, [f[i] for i in range(qo.Q)]).sum(), rtol=1e-14)
