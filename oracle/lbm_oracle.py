@@ -280,7 +280,9 @@ class MRT:
 
     def __init__(self, q, taus, force=None):
         if np.isscalar(taus):
-            taus = [float(taus)] * q.N  # MRT(q, tau): mrt.jl:19-22 (force dropped there)
+            # MRT(q, tau): N = round(Int, order(q) / 2) -- half-to-even, so 4 entries for order 7
+            # (mrt.jl:19-22; `force` is dropped there)
+            taus = [float(taus)] * round(q.order / 2)
         self.taus = [float(t) for t in taus]
         self.force = force
 

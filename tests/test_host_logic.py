@@ -99,7 +99,9 @@ def test_collision_model_factories():
     t3 = lbm.TRT(0.6, 0.9, None)
     assert (t3.tau_symmetric, t3.tau_asymmetric) == (0.6, 0.9)
     assert lbm.MRT(lbm.D2Q37(), 0.8).taus() == [0.8] * 4
-    assert lbm.MRT(lbm.D2Q17(), 0.8, 0.9).taus() == [0.8, 0.9, 0.8]
+    # N = round(Int, order(q) / 2) rounds half to even: order 7 -> 4 relaxation times (mrt.jl:20,25)
+    assert lbm.MRT(lbm.D2Q17(), 0.8, 0.9).taus() == [0.8, 0.9, 0.8, 0.9]
+    assert lbm.MRT(lbm.D2Q4(), 0.8).taus() == [0.8, 0.8]
     assert lbm.MRT(q, 0.8, lambda x, y, t: [1, 1]).force is None  # scalar form drops the force (mrt.jl:19-22)
     assert lbm.MRT(q, [0.8, 0.9], "F").force == "F"
     default = lbm.CollisionModel(lbm.collision_models.CollisionModelBase, q, pr)
