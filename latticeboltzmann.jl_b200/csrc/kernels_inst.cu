@@ -231,11 +231,20 @@ __device__ __forceinline__ int launched_row(const KParams<T> &p, int r) {
 // ------------------------------------------------------------------------------------------
 // moments and equilibrium
 // ------------------------------------------------------------------------------------------
+// Float32 contexts store the deviation g_i = f_i - w_i ("shifted populations") and do all
+// arithmetic on deviations: rho = 1 + sum(g), j = sum(g c) (sum(w c) = 0), feq_i - w_i =
+// w_i (drho + rho P_i(u)) with P the equilibrium polynomial without its leading 1.  This keeps
+// ~7 significant digits on the O(1e-4) velocities instead of losing them against f ~ w.
 template <typename T>
-__device__ __forceinline__ void rho_u(const T (&f)[Q], T &rho, T &ux, T &uy) {
+struct Shifted { static constexpr bool value = std::is_same<T, float>::value; };
+
+template <typename T>
+__device__ __forceinline__ void rho_u(const T (&f)[Q], T &rho, T &ux, T &uy, T &drho) {
     // density = sum(f) (left fold, moments.jl:3); velocity! (moments.jl:5-19)
-    rho = f[0];
-    static_for<1, Q>([&](auto I) { rho = rho + f[decltype(I)::value]; });
+    drho = f[0];
+    static_for<1, Q>([&](auto I) { drho = drho + f[decltype(I)::value]; });
+    if constexpr (Shifted<T>::value) rho = T(1) + drho;
+    else rho = drho;
     T jx = T(0), jy = T(0);
     static_for<0, Q>([&](auto I) {
         constexpr int i = decltype(I)::value;
@@ -253,14 +262,17 @@ template <typename T>
 __device__ __forceinline__ T pow4(T x) { const T x2 = x * x; return x2 * x2; }
 
 // _equilibrium(q, rho, w_i, u.c_i, u.u, T = 1, ...) for compile-time i.
+// Shifted storage: returns feq_i - w_i = w_i (drho + rho (poly - 1)).
 template <int I, typename T>
-__device__ __forceinline__ T feq_i(T rho, T ux, T uy, T u2) {
+__device__ __forceinline__ T feq_i(T rho, T ux, T uy, T u2, T drho) {
     const LatConst<T> &c = LC<T>();
     const T cs = c.css;
     constexpr bool REST = (L::cx(I) == 0 && L::cy(I) == 0);
+    constexpr bool SH = Shifted<T>::value;
     const T udx = cdot<L::cx(I), L::cy(I)>(ux, uy);
     T poly;
-    if constexpr (REST) poly = T(1);
+    if constexpr (REST) poly = SH ? T(0) : T(1);
+    else if constexpr (SH) poly = cs * udx;
     else poly = T(1) + cs * udx;
     if constexpr (L::EQ_ORDER >= 2) {
         T a2;
@@ -278,7 +290,8 @@ __device__ __forceinline__ T feq_i(T rho, T ux, T uy, T u2) {
         else a4 = ((pow4(cs) * pow4(udx)) - ((6 * (cs * cs * cs)) * u2) * (udx * udx)) + (3 * (cs * cs)) * (u2 * u2);
         poly = poly + T(1.0 / 24) * a4;
     }
-    return (rho * c.w[I]) * poly;
+    if constexpr (SH) return c.w[I] * (drho + rho * poly);
+    else return (rho * c.w[I]) * poly;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -286,8 +299,8 @@ __device__ __forceinline__ T feq_i(T rho, T ux, T uy, T u2) {
 // ------------------------------------------------------------------------------------------
 template <int CM, typename T>
 __device__ __forceinline__ void collide_node(const KParams<T> &p, const T (&f)[Q], bool forced, T Fx, T Fy, T (&out)[Q]) {
-    T rho, ux, uy;
-    rho_u(f, rho, ux, uy);
+    T rho, ux, uy, drho;
+    rho_u(f, rho, ux, uy, drho);
     if (forced) {  // equilibrium velocity shift u + tau F (srt.jl:54, trt.jl:79, mrt.jl:94)
         ux = ux + p.shift * Fx;
         uy = uy + p.shift * Fy;
@@ -296,12 +309,12 @@ __device__ __forceinline__ void collide_node(const KParams<T> &p, const T (&f)[Q
         const T u2 = ux * ux + uy * uy;
         static_for<0, Q>([&](auto I) {
             constexpr int i = decltype(I)::value;
-            out[i] = p.c[0] * f[i] + p.c[1] * feq_i<i>(rho, ux, uy, u2);  // srt.jl:58
+            out[i] = p.c[0] * f[i] + p.c[1] * feq_i<i>(rho, ux, uy, u2, drho);  // srt.jl:58
         });
     } else if constexpr (CM == LBM_TRT) {
         const T u2 = ux * ux + uy * uy;
         T feq[Q];
-        static_for<0, Q>([&](auto I) { feq[decltype(I)::value] = feq_i<decltype(I)::value>(rho, ux, uy, u2); });
+        static_for<0, Q>([&](auto I) { feq[decltype(I)::value] = feq_i<decltype(I)::value>(rho, ux, uy, u2, drho); });
         static_for<0, Q>([&](auto I) {  // trt.jl:82-94
             constexpr int i = decltype(I)::value;
             constexpr int o = L::opp(i);
@@ -359,7 +372,8 @@ __device__ __forceinline__ void collide_node(const KParams<T> &p, const T (&f)[Q
         const T csrho = c.css * rho;
         static_for<0, Q>([&](auto I) {  // mrt.jl:107-114
             constexpr int i = decltype(I)::value;
-            T acc = rho + csrho * cdot<L::cx(i), L::cy(i)>(ux, uy);
+            // shifted storage: sum(w H_n) = 0 for n <= N, so a_f is the projection of g and out - w = w (drho + ...)
+            T acc = (Shifted<T>::value ? drho : rho) + csrho * cdot<L::cx(i), L::cy(i)>(ux, uy);
             if constexpr (NH >= 2) {
                 T hs = a2[0] * c.H2[i][0];
                 hs = hs + a2[1] * c.H2[i][1];
@@ -484,8 +498,13 @@ __device__ __forceinline__ void node_fields(const KParams<T> &p, int x, int y, d
     T f[Q];
     load_node<T, PULL>(p, x, y, f);
     double g[Q];
-    static_for<0, Q>([&](auto I) { g[decltype(I)::value] = (double)f[decltype(I)::value]; });
-    rho_u<double>(g, rho, ux, uy);
+    static_for<0, Q>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        if constexpr (Shifted<T>::value) g[i] = (double)f[i] + c_lat64.w[i];
+        else g[i] = (double)f[i];
+    });
+    double drho_unused;
+    rho_u<double>(g, rho, ux, uy, drho_unused);
     // a_bar_2 = sum(f[idx] * hermite(Val{2}, c_idx, q))  (moments.jl:27-28, 90-92), left fold
     const LatConst<double> &c = c_lat64;
     axx = g[0] * c.H2[0][0]; axy = g[0] * c.H2[0][1]; ayy = g[0] * c.H2[0][2];
@@ -582,6 +601,20 @@ __global__ void k_reduce_final(const ReduceArgs ra) {
     }
 }
 
+// Float32 storage <-> host Float64 planes: g = (float)(f - w), f = (double)g + w
+__global__ void __launch_bounds__(256) k_import32(const __grid_constant__ KParams<float> p, const double *stage, int i) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= p.nx) return;
+    for (int y = blockIdx.y * blockDim.y + threadIdx.y; y < p.nyl; y += gridDim.y * blockDim.y)
+        p.dst[i * p.plane + (long long)y * p.pitch + x] = (float)(stage[(long long)y * p.nx + x] - c_lat64.w[i]);
+}
+__global__ void __launch_bounds__(256) k_export32(const __grid_constant__ KParams<float> p, double *stage, int i) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= p.nx) return;
+    for (int y = blockIdx.y * blockDim.y + threadIdx.y; y < p.nyl; y += gridDim.y * blockDim.y)
+        stage[(long long)y * p.nx + x] = (double)p.src[i * p.plane + (long long)y * p.pitch + x] + c_lat64.w[i];
+}
+
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
@@ -654,15 +687,24 @@ static void launch_reduce(bool pull, const KParams<T> &p, const ReduceArgs &r, c
     k_reduce_final<<<1, 32, 0, s>>>(ra);
 }
 
+static void launch_import32(const KParams<float> &p, const double *stage, int i, cudaStream_t s) {
+    dim3 block; pick_block(p.nx, block);
+    k_import32<<<grid_for(p, block, p.nyl, p.nx), block, 0, s>>>(p, stage, i);
+}
+static void launch_export32(const KParams<float> &p, double *stage, int i, cudaStream_t s) {
+    dim3 block; pick_block(p.nx, block);
+    k_export32<<<grid_for(p, block, p.nyl, p.nx), block, 0, s>>>(p, stage, i);
+}
+
 static const Ops ops = {
     LBM_LATTICE, LBM_FAST,
-    &launch_step<double>, nullptr,
-    &launch_stream<double>, nullptr,
-    &launch_bcs<double>, nullptr,
-    &launch_ghosts<double>, nullptr,
-    &launch_moments<double>, nullptr,
-    &launch_reduce<double>, nullptr,
-    nullptr, nullptr,
+    &launch_step<double>, &launch_step<float>,
+    &launch_stream<double>, &launch_stream<float>,
+    &launch_bcs<double>, &launch_bcs<float>,
+    &launch_ghosts<double>, &launch_ghosts<float>,
+    &launch_moments<double>, &launch_moments<float>,
+    &launch_reduce<double>, &launch_reduce<float>,
+    &launch_import32, &launch_export32,
     &init_constants,
 };
 

@@ -368,3 +368,76 @@ def test_error_paths():
             c.stream()  # stream! before collide!
         with pytest.raises(ValueError):
             c.upload_f(np.zeros((8, 8, 5)))
+
+
+# ---------------------------------------------------------------------------------------------
+# Float32 (new capability: the reference is Float64-only).  Storage = f - w, arithmetic on deviations.
+# Tolerance from BASELINE.json north_star: 1e-5 relative (max-norm) on populations and moments
+# against the Float64 oracle.
+# ---------------------------------------------------------------------------------------------
+TOL32 = 1e-5
+
+
+@pytest.mark.parametrize("name", LATTICES)
+@pytest.mark.parametrize("model", ["SRT", "TRT", "MRT"])
+@pytest.mark.parametrize("arith", [_abi.ARITH_EXACT, _abi.ARITH_FAST])
+def test_f32_steps_match_f64_oracle(oracle, name, model, arith):
+    O = oracle
+    qo = O.L.BY_NAME[name]()
+    nx, ny, nsteps = 24, 16, 20
+    # smooth Taylor-Green-like start, u ~ 1e-3
+    pr = O.TGV(qo, 0.8, 1, nx, ny, u_max=2e-3)
+    f0 = O.initialize("AnalyticalEquilibrium", qo, pr)
+    force = (1e-6, -1e-6)
+    cm, code, taus = _models(O, qo, force)[model]
+    ob, hb = _bcs_pair(O, "couette" if name in ("D2Q9", "D2Q37") else "none", nx, ny)
+    want = f0.copy()
+    for _ in range(nsteps):
+        want, _ = O.step(cm, qo, ob, want)
+    with _ctx(name, code, taus, hb, nx, ny, arith, dtype=_abi.F32) as c:
+        c.set_force_uniform(*force)
+        c.upload_f(to_host_layout(f0))
+        back = to_oracle_layout(c.download_f())
+        c.step(0, nsteps)
+        got = to_oracle_layout(c.download_f())
+        m = c.moments(0.3, ("rho", "ux", "uy"))
+    # storage round trip keeps the deviation to Float32 precision
+    dev = np.abs(f0 - qo.w[:, None, None]).max()
+    assert np.abs(back - f0).max() <= 1.2e-7 * dev + 1e-12
+    assert rel_max(got, want) < TOL32
+    fl = [want[i] for i in range(qo.Q)]
+    rho = O.density(qo, fl)
+    ux, uy = O.velocity(qo, fl, rho)
+    assert rel_max(m["rho"].T, rho) < TOL32
+    scale = max(np.abs(ux).max(), np.abs(uy).max())
+    assert np.abs(m["ux"].T - ux).max() < TOL32 * scale and np.abs(m["uy"].T - uy).max() < TOL32 * scale
+
+
+def test_f32_config_c2_crop_100_steps(oracle):
+    """BASELINE config 2 physics (D2Q9 TRT TGV, tau = 0.8, Lambda = 1/4) on a 256^2 crop, 100 steps:
+    Float32 velocities within 1e-5 of the Float64 oracle; Float64 within 1e-12 (bit-identical here)."""
+    O = oracle
+    from oracle.c_oracle import COracle
+    qo = O.L.D2Q9()
+    n = 256
+    pr = O.TGV(qo, 0.8, n // 16)
+    f0 = O.initialize("AnalyticalEquilibrium", qo, pr)
+    cm = O.collision_model("TRT", qo, pr)
+    want, _ = COracle(qo, cm).steps(f0, 100)
+    fl = [want[i] for i in range(qo.Q)]
+    rho = O.density(qo, fl)
+    ux, uy = O.velocity(qo, fl, rho)
+    q = lbm.D2Q9()
+    hp = lbm.TGV(q, 0.8, n // 16)
+    for dtype, tol in (("f64", 1e-12), ("f32", TOL32)):
+        for arith in ("exact", "fast"):
+            m = lbm.LatticeBoltzmannModel(hp, q, collision_model=lbm.TRT, dtype=dtype, arith=arith)
+            m.f_stream = to_host_layout(f0)
+            m.state.step(0, 100, 1.0)
+            got = to_oracle_layout(m.f_stream)
+            mo = m.ctx.moments(1.0, ("ux", "uy"))
+            m.close()
+            assert rel_max(got, want) < tol, (dtype, arith)
+            assert rel_max(mo["ux"].T, ux) < tol and rel_max(mo["uy"].T, uy) < tol, (dtype, arith)
+            if dtype == "f64" and arith == "exact":
+                assert np.array_equal(got, want)
