@@ -417,8 +417,9 @@ __device__ __forceinline__ bool load_force(const KParams<T> &p, int x, int y, lo
 // ------------------------------------------------------------------------------------------
 // K1/K2: collide, optionally fused with the pull (stream + BCs) of the previous step
 // ------------------------------------------------------------------------------------------
-template <int CM, typename T, bool PULL>
-__global__ void __launch_bounds__(256) k_step(const __grid_constant__ KParams<T> p, long long step) {
+// MINB: minimum resident CTAs per SM asked of the register allocator (occupancy tuning knob).
+template <int CM, typename T, bool PULL, int MINB = 1>
+__global__ void __launch_bounds__(256, MINB) k_step(const __grid_constant__ KParams<T> p, long long step) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= p.nx) return;
     for (int r = blockIdx.y * blockDim.y + threadIdx.y; r < p.nrows; r += gridDim.y * blockDim.y) {
@@ -632,15 +633,29 @@ static inline dim3 grid_for(const KParams<T> &p, const dim3 &block, int rows, in
     return dim3((cols + block.x - 1) / block.x, gy, 1);
 }
 
+// Default register budget: ask for enough resident CTAs that narrow lattices stay at <= 64
+// registers/thread; wide lattices need the registers for their 17..37 populations.
+constexpr int DEFAULT_MINB = (Q <= 13) ? 4 : ((Q <= 25) ? 2 : 1);
+
 template <typename T>
 static void launch_step(int cm, bool pull, const KParams<T> &p, long long step, int variant, cudaStream_t s) {
-    (void)variant;
     if (p.nrows <= 0) return;
     dim3 block; pick_block(p.nx, block);
+    if (variant >= 100) {  // tuning: 128-thread CTAs
+        variant -= 100;
+        if (block.x >= 128) block = dim3(128, 1, 1);
+    }
     dim3 grid = grid_for(p, block, p.nrows, p.nx);
-#define LBM_LAUNCH(CM)                                                         \
-    if (pull) k_step<CM, T, true><<<grid, block, 0, s>>>(p, step);             \
-    else k_step<CM, T, false><<<grid, block, 0, s>>>(p, step);
+#ifdef LBM_TUNE
+#define LBM_TUNE_CASE(CM, MB) case MB: k_step<CM, T, true, MB><<<grid, block, 0, s>>>(p, step); return;
+#define LBM_TUNE_CM(CM)                                                                                        \
+    if (cm == CM) switch (variant) { LBM_TUNE_CASE(CM, 1) LBM_TUNE_CASE(CM, 2) LBM_TUNE_CASE(CM, 3)            \
+                                     LBM_TUNE_CASE(CM, 4) LBM_TUNE_CASE(CM, 5) LBM_TUNE_CASE(CM, 6) default: break; }
+    if (pull && variant > 0) { LBM_TUNE_CM(LBM_SRT) LBM_TUNE_CM(LBM_TRT) LBM_TUNE_CM(LBM_MRT) }
+#endif
+#define LBM_LAUNCH(CM)                                                                       \
+    if (pull) k_step<CM, T, true, DEFAULT_MINB><<<grid, block, 0, s>>>(p, step);             \
+    else k_step<CM, T, false, DEFAULT_MINB><<<grid, block, 0, s>>>(p, step);
     switch (cm) {
     case LBM_SRT: LBM_LAUNCH(LBM_SRT) break;
     case LBM_TRT: LBM_LAUNCH(LBM_TRT) break;
