@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--lattice", default="D2Q9")
     ap.add_argument("--collision", default="TRT", choices=["SRT", "TRT", "MRT"])
     ap.add_argument("--variant", type=int, default=int(os.environ.get("LBM_BENCH_VARIANT", "0")))
+    ap.add_argument("--config", default="C2", choices=["C2", "C3", "C4", "C5s", "C5w"],
+                    help="BASELINE.json config preset (C2 = default bench workload; see build_case)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-n", type=int, default=1024)
@@ -159,6 +161,43 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
+def build_case(a, world, lbm):
+    """BASELINE.json configs as concrete problems (inputs: SURVEY.md section 8d)."""
+    Qs = {"D2Q4": lbm.D2Q4, "D2Q5": lbm.D2Q5, "D2Q9": lbm.D2Q9, "D2Q13": lbm.D2Q13, "D2Q17": lbm.D2Q17,
+          "D2Q21": lbm.D2Q21, "D2Q37": lbm.D2Q37}
+    CMs = {"SRT": lbm.SRT, "TRT": lbm.TRT, "MRT": lbm.MRT}
+    if a.config in ("C2", "C5w", "C5s"):
+        # TGV(q, tau = 0.8, scale) Taylor-Green vortex decay, periodic; CollisionModel(TRT): Lambda = 1/4
+        q = Qs[a.lattice]()
+        if a.config == "C2":
+            nx, ny, scaling = a.nx, a.ny * world, "weak"
+        elif a.config == "C5w":
+            nx, ny, scaling = 16384, 16384 * world, "weak"
+        else:
+            nx, ny, scaling = 32768, 32768, "strong"
+        problem = lbm.TGV(q, 0.8, max(nx // 16, 1), nx, ny)
+        cm = lbm.CollisionModel(CMs[a.collision], q, problem)
+        name = f"{a.lattice} {a.collision} Taylor-Green vortex decay, periodic (BASELINE configs[{1 if a.config == 'C2' else 4}])"
+        return dict(q=q, problem=problem, cm=cm, nx=nx, ny=ny, scaling=scaling, init=lbm.AnalyticalEquilibrium(),
+                    workload=name)
+    if a.config == "C3":
+        # D2Q9 SRT + uniform force Poiseuille channel 1024 x 8192, bounce-back North + South (strong scaling)
+        q = lbm.D2Q9()
+        nx, ny = 1024, 8192
+        problem = lbm.PoiseuilleFlow.fields(1.0, 0.1 / (ny / 5), 1 / 6, nx, ny, 1.0, (1.0, 1.0), 1.0)
+        cm = lbm.CollisionModel(lbm.SRT, q, problem)
+        return dict(q=q, problem=problem, cm=cm, nx=nx, ny=ny, scaling="strong",
+                    init=lbm.ZeroVelocityInitialCondition(),
+                    workload="D2Q9 SRT+force Poiseuille, bounce-back walls, 1024x8192 (BASELINE configs[2])")
+    # C4: D2Q37 TRT Couette 8192^2, bounce-back South + moving wall North, halo width 3 (strong scaling)
+    q = lbm.D2Q37()
+    nx = ny = 8192
+    problem = lbm.CouetteFlow.fields(1.0, 0.01 / (ny / 5), 0.3 / q.speed_of_sound_squared, nx, ny, (1.0, 1.0))
+    cm = lbm.CollisionModel(lbm.TRT, q, problem)
+    return dict(q=q, problem=problem, cm=cm, nx=nx, ny=ny, scaling="strong", init=lbm.ZeroVelocityInitialCondition(),
+                workload="D2Q37 TRT Couette, moving wall North + bounce-back South, 8192x8192 (BASELINE configs[3])")
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -170,6 +209,8 @@ def ncu_traffic(a):
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         t = json.load(open(p))
+        if a.config != "C2":
+            return None
         key = f"{a.lattice}_{a.collision}_{a.dtype}_{a.arith}_{a.nx}x{a.ny}"
         return t.get(key)
     return None
@@ -192,21 +233,32 @@ def run_b200(a):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         comm = lbm.SlabComm()
-    nx, nyl, inner = a.nx, a.ny, a.inner
-    ny = nyl * world
-    q = {"D2Q4": lbm.D2Q4, "D2Q5": lbm.D2Q5, "D2Q9": lbm.D2Q9, "D2Q13": lbm.D2Q13, "D2Q17": lbm.D2Q17,
-         "D2Q21": lbm.D2Q21, "D2Q37": lbm.D2Q37}[a.lattice]()
-    problem = lbm.TGV(q, 0.8, max(nx // 16, 1), nx, ny)
-    cm = lbm.CollisionModel({"SRT": lbm.SRT, "TRT": lbm.TRT, "MRT": lbm.MRT}[a.collision], q, problem)
-    ctx = lbm.model.make_context(q, cm, [], nx, ny, a.dtype, a.arith, comm, local)
+    inner = a.inner
+    case = build_case(a, world, lbm)
+    q, problem, cm, nx, ny, scaling = case["q"], case["problem"], case["cm"], case["nx"], case["ny"], case["scaling"]
+    ctx = lbm.model.make_context(q, cm, problem.boundary_conditions(), nx, ny, a.dtype, a.arith, comm, local)
     ctx.set_option("variant", a.variant)
-    assert ctx.ny_local == nyl
-    # synthetic input: analytic Taylor-Green equilibrium of this rank's slab, in pinned host memory
-    pinned = torch.empty(nx * nyl * q.Q, dtype=torch.float64, pin_memory=True)
-    host = pinned.numpy().reshape((nx, nyl, q.Q), order="F")
-    host[...] = lbm.initialize(lbm.AnalyticalEquilibrium(), q, problem, rows=(ctx.y0, nyl))
-    ctx.upload_f(host)
-    ctx.set_force_none()
+    nyl = ctx.ny_local
+    state = lbm.DeviceState(ctx, q, cm, comm)
+    state.prepare_force(0, 1, problem.delta_t())
+    # synthetic input: the problem's analytic initial condition for this rank's slab.  Small slabs live
+    # in ONE pinned host array (also used by the e2e leg); huge ones are generated chunk by chunk.
+    slab_bytes = nx * nyl * q.Q * 8
+    do_e2e = (not a.no_e2e) and slab_bytes <= (8 << 30)
+    host = None
+    if do_e2e:
+        pinned = torch.empty(nx * nyl * q.Q, dtype=torch.float64, pin_memory=True)
+        host = pinned.numpy().reshape((nx, nyl, q.Q), order="F")
+    chunk = max(1, min(nyl, (64 << 20) // max(nx, 1)))
+    for off in range(0, nyl, chunk):
+        n = min(chunk, nyl - off)
+        block = lbm.initialize(case["init"], q, problem, rows=(ctx.y0 + off, n))
+        if host is not None:
+            host[:, off:off + n, :] = block
+        else:
+            ctx.upload_f_rows(off, block)
+    if host is not None:
+        ctx.upload_f(host)
 
     def barrier():
         ctx.sync()
@@ -249,7 +301,7 @@ def run_b200(a):
 
     # ---- e2e: host buffers in and out through the C ABI --------------------------------------
     e2e = None
-    if not a.no_e2e:
+    if do_e2e:
         out_pinned = torch.empty(nx * nyl * q.Q, dtype=torch.float64, pin_memory=True)
         out_host = out_pinned.numpy().reshape((nx, nyl, q.Q), order="F")
         n_e2e = max(2, min(a.steps, 5))
@@ -274,16 +326,16 @@ def run_b200(a):
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu:
-        v, threads, secs = cpu_restatement_mlups(a.cpu_n, a.cpu_steps, a.lattice, a.collision)
+        v, threads, secs = cpu_restatement_mlups(a.cpu_n, a.cpu_steps, q.name, type(cm).__name__)
         cpu = {"value": v, "unit": "MLUPS", "cores": threads, "kind": "port",
                "sample": f"{a.cpu_n}x{a.cpu_n} crop, {a.cpu_steps} lattice steps ({secs:.1f} s), C restatement "
                          f"(oracle/lbm_oracle.c) with OpenMP over rows"}
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "MLUPS", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
-            "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": a.dtype, "data": "synthetic",
-            "config": {"workload": f"{a.lattice} {a.collision} Taylor-Green vortex decay, periodic (BASELINE configs[1])",
+            "config": {"workload": case["workload"], "preset": a.config,
                        "grid_per_gpu": [nx, nyl], "grid_global": [nx, ny], "lattice_steps_per_bench_step": inner,
                        "arith": a.arith, "variant": a.variant, "parallelism": f"y-slabs x{world}",
                        "l2": "working set (2 x %.2f GB per GPU) >> 126 MB L2; no flush needed" % (nx * nyl * q.Q * BYTES[a.dtype] / 1e9),
@@ -293,7 +345,7 @@ def run_b200(a):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "bytes_per_update": b_alg,
-                         "kernel_ms": kern_ms, "kernel": "k_step<%s, %s, pull>" % (a.collision, a.dtype)},
+                         "kernel_ms": kern_ms, "kernel": "k_step<%s, %s, pull>" % (type(cm).__name__, a.dtype)},
             "cpu_baseline": cpu,
         }))
     ctx.close()

@@ -114,6 +114,10 @@ int lbm_upload_f(lbm_ctx *ctx, const double *f);
  * (stream!(q, f, f_new), apply!(bcs, q, f_new, f_old)); call after lbm_upload_f. */
 int lbm_upload_f_collision(lbm_ctx *ctx, const double *f);
 int lbm_download_f(lbm_ctx *ctx, double *f);
+/* The same for a block of rows [y0, y0+ny) of the local slab (host array [q][ny][nx]): lets the
+ * host initialise / read grids larger than its own memory chunk by chunk (32768^2: 77 GB). */
+int lbm_upload_f_rows(lbm_ctx *ctx, int32_t y0, int32_t ny, const double *f_rows);
+int lbm_download_f_rows(lbm_ctx *ctx, int32_t y0, int32_t ny, double *f_rows);
 int lbm_download_f_collision(lbm_ctx *ctx, double *f);
 
 /* The force closure `collision_model.force(x_idx, y_idx, time)` (srt.jl:10-12,52; trt.jl:17-18,77;

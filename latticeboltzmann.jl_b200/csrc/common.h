@@ -23,6 +23,14 @@ struct KParams {
     const T *src;  // pulled / read buffer
     T *dst;        // written buffer
     const T *aux;  // f_old (post-collision) for the standalone BC kernel
+    // per-plane base pointers so that a node address is ONE 32-bit multiply-add per population:
+    //   srcn[i] = src + i*plane                       (unshifted)
+    //   srcp[i] = src + i*plane - c_y[i]*pitch - c_x[i] (pull source of population i)
+    //   dstp[i] = dst + i*plane
+    // indexed with the node offset n = y*pitch + x (< 2^31, checked by lbm_create)
+    const T *srcn[LBM_MAX_Q];
+    const T *srcp[LBM_MAX_Q];
+    T *dstp[LBM_MAX_Q];
     long long pitch, plane;
     int nx, nyl;   // local interior size
     int y0g, nyg;  // first global row of this slab, global row count

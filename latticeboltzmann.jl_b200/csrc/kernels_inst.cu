@@ -169,14 +169,11 @@ __device__ __forceinline__ T bounced(const KParams<T> &p, int b, T f_opp) {
 //               condition overwrites it with src[opp(i), y, x].
 template <typename T, bool PULL>
 __device__ __forceinline__ void load_node(const KParams<T> &p, int x, int y, T (&f)[Q]) {
-    const T *base = p.src + (long long)y * p.pitch + x;
+    const unsigned n = (unsigned)y * (unsigned)p.pitch + (unsigned)x;
     static_for<0, Q>([&](auto I) {
         constexpr int i = decltype(I)::value;
-        if constexpr (PULL) {
-            f[i] = __ldg(base + (i * p.plane - L::cy(i) * p.pitch - L::cx(i)));
-        } else {
-            f[i] = __ldg(base + i * p.plane);
-        }
+        if constexpr (PULL) f[i] = __ldg(p.srcp[i] + n);
+        else f[i] = __ldg(p.srcn[i] + n);
     });
     if constexpr (PULL) {
         const int yg = p.y0g + y;
@@ -186,41 +183,43 @@ __device__ __forceinline__ void load_node(const KParams<T> &p, int x, int y, T (
                 constexpr int o = L::opp(i);
                 if constexpr (i != o) {
                     const int b = resolve_bc(p, x + 1, yg + 1, L::cx(o), L::cy(o));
-                    if (b >= 0) f[i] = bounced<i>(p, b, __ldg(base + o * p.plane));
+                    if (b >= 0) f[i] = bounced<i>(p, b, __ldg(p.srcn[o] + n));
                 }
             });
         }
     }
 }
 
-// Stores the node and, for nodes within H of the slab edge, its periodic images inside the
-// ghost frame (all planes share the offsets).  Image loops are runtime, population loops unrolled,
-// so `out` stays in registers.
+// After a node has been stored: copy it to its periodic images inside the ghost frame (edge
+// threads only; all planes share the offsets).  The values are read back from dst (the thread's own
+// stores, L1/L2 hits) so that the collision outputs need not stay in registers.
+template <typename T>
+__device__ __forceinline__ void store_images(const KParams<T> &p, int x, int y) {
+    const bool ex = (x < H) || (x >= p.nx - H);
+    const bool ey = p.wrap_y && ((y < H) || (y >= p.nyl - H));
+    if (ex || ey) {
+        T *d = p.dst + (long long)y * p.pitch + x;
+        const int kx_lo = -((x + H) / p.nx), kx_hi = (p.nx + H - 1 - x) / p.nx;
+        int ky_lo = 0, ky_hi = 0;
+        if (p.wrap_y) { ky_lo = -((y + H) / p.nyl); ky_hi = (p.nyl + H - 1 - y) / p.nyl; }
+        for (int ky = ky_lo; ky <= ky_hi; ++ky)
+            for (int kx = kx_lo; kx <= kx_hi; ++kx) {
+                if (kx == 0 && ky == 0) continue;
+                T *g = d + (long long)(ky * p.nyl) * p.pitch + kx * p.nx;
+#pragma unroll 1
+                for (int i = 0; i < Q; ++i) g[i * p.plane] = d[i * p.plane];
+            }
+    }
+}
+
 template <typename T, bool GHOSTS>
 __device__ __forceinline__ void store_node(const KParams<T> &p, int x, int y, T (&out)[Q]) {
-    T *d = p.dst + (long long)y * p.pitch + x;
+    const unsigned n = (unsigned)y * (unsigned)p.pitch + (unsigned)x;
     static_for<0, Q>([&](auto I) {
         constexpr int i = decltype(I)::value;
-        d[i * p.plane] = out[i];
+        p.dstp[i][n] = out[i];
     });
-    if constexpr (GHOSTS) {
-        const bool ex = (x < H) || (x >= p.nx - H);
-        const bool ey = p.wrap_y && ((y < H) || (y >= p.nyl - H));
-        if (ex || ey) {
-            const int kx_lo = -((x + H) / p.nx), kx_hi = (p.nx + H - 1 - x) / p.nx;
-            int ky_lo = 0, ky_hi = 0;
-            if (p.wrap_y) { ky_lo = -((y + H) / p.nyl); ky_hi = (p.nyl + H - 1 - y) / p.nyl; }
-            for (int ky = ky_lo; ky <= ky_hi; ++ky)
-                for (int kx = kx_lo; kx <= kx_hi; ++kx) {
-                    if (kx == 0 && ky == 0) continue;
-                    T *g = d + (long long)(ky * p.nyl) * p.pitch + kx * p.nx;
-                    static_for<0, Q>([&](auto I) {
-                        constexpr int i = decltype(I)::value;
-                        g[i * p.plane] = out[i];
-                    });
-                }
-        }
-    }
+    if constexpr (GHOSTS) store_images(p, x, y);
 }
 
 template <typename T>
@@ -294,11 +293,38 @@ __device__ __forceinline__ T feq_i(T rho, T ux, T uy, T u2, T drho) {
     else return (rho * c.w[I]) * poly;
 }
 
+// fast mode only: symmetric / antisymmetric parts of the pair (i, opp(i)) directly --
+//   feq_s = rho w (1 + a2/2 + a4/24),  feq_a = rho w (a1 + a3/6)   (a1, a3 odd in c.u; a2, a4 even)
+// (shifted storage: feq_s - w = w (drho + rho (a2/2 + a4/24))).  Same polynomial as feq_i, fewer
+// operations, different rounding -- which is why the exact mode does not use it.
+template <int I, typename T>
+__device__ __forceinline__ void feq_sym_asym(T rho, T ux, T uy, T u2, T drho, T &es, T &ea) {
+    const LatConst<T> &c = LC<T>();
+    const T cs = c.css;
+    constexpr bool SH = Shifted<T>::value;
+    const T udx = cdot<L::cx(I), L::cy(I)>(ux, uy);
+    const T a1 = cs * udx;
+    T even = SH ? T(0) : T(1);
+    T odd = a1;
+    if constexpr (L::EQ_ORDER >= 2) even = even + T(0.5) * (a1 * a1 - cs * u2);
+    if constexpr (L::EQ_ORDER >= 3) odd = odd + T(1.0 / 6) * (a1 * (a1 * a1 - (3 * cs) * u2));
+    if constexpr (L::EQ_ORDER >= 4) {
+        const T b = cs * u2;
+        even = even + T(1.0 / 24) * ((a1 * a1) * (a1 * a1 - 6 * b) + 3 * (b * b));
+    }
+    const T rw = rho * c.w[I];
+    if constexpr (SH) es = c.w[I] * drho + rw * even;
+    else es = rw * even;
+    ea = rw * odd;
+}
+
 // ------------------------------------------------------------------------------------------
 // collision operators (Float64 / raw populations)
 // ------------------------------------------------------------------------------------------
-template <int CM, typename T>
-__device__ __forceinline__ void collide_node(const KParams<T> &p, const T (&f)[Q], bool forced, T Fx, T Fy, T (&out)[Q]) {
+// `emit(I, value)` receives each post-collision population as soon as it is known (it is stored
+// right away, so no second Q-sized array is live).
+template <int CM, typename T, class Emit>
+__device__ __forceinline__ void collide_node(const KParams<T> &p, const T (&f)[Q], bool forced, T Fx, T Fy, Emit &&emit) {
     T rho, ux, uy, drho;
     rho_u(f, rho, ux, uy, drho);
     if (forced) {  // equilibrium velocity shift u + tau F (srt.jl:54, trt.jl:79, mrt.jl:94)
@@ -309,20 +335,35 @@ __device__ __forceinline__ void collide_node(const KParams<T> &p, const T (&f)[Q
         const T u2 = ux * ux + uy * uy;
         static_for<0, Q>([&](auto I) {
             constexpr int i = decltype(I)::value;
-            out[i] = p.c[0] * f[i] + p.c[1] * feq_i<i>(rho, ux, uy, u2, drho);  // srt.jl:58
+            emit(I, p.c[0] * f[i] + p.c[1] * feq_i<i>(rho, ux, uy, u2, drho));  // srt.jl:58
         });
     } else if constexpr (CM == LBM_TRT) {
+        // trt.jl:82-94, processed per pair (i, opp(i)) so that only f (not a second array of feq)
+        // stays live.  Bit-identical to the per-population form: f_s, feq_s are symmetric in
+        // (i, o) and f_a, feq_a change sign exactly.
         const T u2 = ux * ux + uy * uy;
-        T feq[Q];
-        static_for<0, Q>([&](auto I) { feq[decltype(I)::value] = feq_i<decltype(I)::value>(rho, ux, uy, u2, drho); });
-        static_for<0, Q>([&](auto I) {  // trt.jl:82-94
+        static_for<0, Q>([&](auto I) {
             constexpr int i = decltype(I)::value;
             constexpr int o = L::opp(i);
-            const T feq_s = T(0.5) * (feq[i] + feq[o]);
-            const T feq_a = T(0.5) * (feq[i] - feq[o]);
-            const T f_s = T(0.5) * (f[i] + f[o]);
-            const T f_a = T(0.5) * (f[i] - f[o]);
-            out[i] = f[i] + (p.c[0] * (f_s - feq_s) - p.c[1] * (f_a - feq_a));
+            if constexpr (i == o) {
+                const T fe = feq_i<i>(rho, ux, uy, u2, drho);
+                const T feq_s = T(0.5) * (fe + fe), feq_a = T(0.5) * (fe - fe);
+                const T f_s = T(0.5) * (f[i] + f[i]), f_a = T(0.5) * (f[i] - f[i]);
+                emit(I, f[i] + (p.c[0] * (f_s - feq_s) - p.c[1] * (f_a - feq_a)));
+            } else if constexpr (i < o) {
+                T feq_s, feq_a;
+                if constexpr (LBM_FAST) {
+                    feq_sym_asym<i>(rho, ux, uy, u2, drho, feq_s, feq_a);
+                } else {
+                    const T fi = feq_i<i>(rho, ux, uy, u2, drho), fo = feq_i<o>(rho, ux, uy, u2, drho);
+                    feq_s = T(0.5) * (fi + fo);
+                    feq_a = T(0.5) * (fi - fo);
+                }
+                const T f_s = T(0.5) * (f[i] + f[o]), f_a = T(0.5) * (f[i] - f[o]);
+                const T s_part = p.c[0] * (f_s - feq_s), a_part = p.c[1] * (f_a - feq_a);
+                emit(I, f[i] + (s_part - a_part));
+                emit(std::integral_constant<int, o>{}, f[o] + (s_part + a_part));
+            }
         });
     } else {
         // regularised MRT (mrt.jl:56-118) with the symmetric tensors reduced to their unique
@@ -388,7 +429,7 @@ __device__ __forceinline__ void collide_node(const KParams<T> &p, const T (&f)[Q
                 }
                 acc = acc + hs;
             }
-            out[i] = c.w[i] * acc;
+            emit(I, c.w[i] * acc);
         });
     }
 }
@@ -417,19 +458,29 @@ __device__ __forceinline__ bool load_force(const KParams<T> &p, int x, int y, lo
 // ------------------------------------------------------------------------------------------
 // K1/K2: collide, optionally fused with the pull (stream + BCs) of the previous step
 // ------------------------------------------------------------------------------------------
-// MINB: minimum resident CTAs per SM asked of the register allocator (occupancy tuning knob).
-template <int CM, typename T, bool PULL, int MINB = 1>
+// MINB: minimum resident CTAs per SM asked of the register allocator; NPT: consecutive rows handled
+// by one thread (all NPT*Q loads are issued before the first use -> more bytes in flight per thread,
+// which is what the 4-byte populations need to cover the HBM latency).
+template <int CM, typename T, bool PULL, int MINB = 1, int NPT = 1>
 __global__ void __launch_bounds__(256, MINB) k_step(const __grid_constant__ KParams<T> p, long long step) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= p.nx) return;
-    for (int r = blockIdx.y * blockDim.y + threadIdx.y; r < p.nrows; r += gridDim.y * blockDim.y) {
-        const int y = launched_row(p, r);
-        T f[Q], out[Q];
-        load_node<T, PULL>(p, x, y, f);
-        T Fx, Fy;
-        const bool forced = load_force(p, x, y, step, Fx, Fy);
-        collide_node<CM, T>(p, f, forced, Fx, Fy, out);
-        store_node<T, true>(p, x, y, out);
+    for (int r0 = (blockIdx.y * blockDim.y + threadIdx.y) * NPT; r0 < p.nrows; r0 += gridDim.y * blockDim.y * NPT) {
+        T f[NPT][Q];
+#pragma unroll
+        for (int j = 0; j < NPT; ++j)
+            if (r0 + j < p.nrows) load_node<T, PULL>(p, x, launched_row(p, r0 + j), f[j]);
+#pragma unroll
+        for (int j = 0; j < NPT; ++j)
+            if (r0 + j < p.nrows) {
+                const int y = launched_row(p, r0 + j);
+                T Fx, Fy;
+                const bool forced = load_force(p, x, y, step, Fx, Fy);
+                const unsigned n = (unsigned)y * (unsigned)p.pitch + (unsigned)x;
+                collide_node<CM, T>(p, f[j], forced, Fx, Fy,
+                                    [&](auto I, T v) { p.dstp[decltype(I)::value][n] = v; });
+                store_images(p, x, y);
+            }
     }
 }
 
@@ -633,29 +684,50 @@ static inline dim3 grid_for(const KParams<T> &p, const dim3 &block, int rows, in
     return dim3((cols + block.x - 1) / block.x, gy, 1);
 }
 
-// Default register budget: ask for enough resident CTAs that narrow lattices stay at <= 64
-// registers/thread; wide lattices need the registers for their 17..37 populations.
-constexpr int DEFAULT_MINB = (Q <= 13) ? 4 : ((Q <= 25) ? 2 : 1);
+// Launch configuration of the fused kernel per <collision model, dtype>: {MINB, NPT, CTA threads},
+// chosen from tools/sweep.py runs on B200 (profiles/r01_sweep_summary.md).
+struct StepCfg { int minb, npt, threads; };
+template <int CM, typename T>
+constexpr StepCfg step_cfg() {
+    if (std::is_same<T, double>::value) {
+        if (Q <= 13) return {4, 1, 256};
+        if (Q <= 17) return {3, 1, 256};
+        return {2, 1, 128};
+    }
+    if (Q <= 9) return {6, 1, 256};
+    if (Q <= 13) return {4, 2, 128};
+    if (Q <= 17) return {5, 1, 128};
+    if (Q <= 25) return {4, 1, 128};
+    return {3, 1, 128};
+}
+
+template <int CM, typename T, bool PULL, int MINB, int NPT>
+static void launch_step_cfg(const KParams<T> &p, long long step, int threads, cudaStream_t s) {
+    dim3 block; pick_block(p.nx, block);
+    if (threads == 128 && block.x >= 128) block = dim3(128, 1, 1);
+    dim3 grid = grid_for(p, block, (p.nrows + NPT - 1) / NPT, p.nx);
+    k_step<CM, T, PULL, MINB, NPT><<<grid, block, 0, s>>>(p, step);
+}
 
 template <typename T>
 static void launch_step(int cm, bool pull, const KParams<T> &p, long long step, int variant, cudaStream_t s) {
     if (p.nrows <= 0) return;
-    dim3 block; pick_block(p.nx, block);
-    if (variant >= 100) {  // tuning: 128-thread CTAs
-        variant -= 100;
-        if (block.x >= 128) block = dim3(128, 1, 1);
-    }
-    dim3 grid = grid_for(p, block, p.nrows, p.nx);
 #ifdef LBM_TUNE
-#define LBM_TUNE_CASE(CM, MB) case MB: k_step<CM, T, true, MB><<<grid, block, 0, s>>>(p, step); return;
-#define LBM_TUNE_CM(CM)                                                                                        \
-    if (cm == CM) switch (variant) { LBM_TUNE_CASE(CM, 1) LBM_TUNE_CASE(CM, 2) LBM_TUNE_CASE(CM, 3)            \
-                                     LBM_TUNE_CASE(CM, 4) LBM_TUNE_CASE(CM, 5) LBM_TUNE_CASE(CM, 6) default: break; }
-    if (pull && variant > 0) { LBM_TUNE_CM(LBM_SRT) LBM_TUNE_CM(LBM_TRT) LBM_TUNE_CM(LBM_MRT) }
+    // variant = MINB + 10 * log2(NPT) + 100 * (128-thread CTAs); 0 = production configuration
+    if (pull && variant > 0) {
+        const int threads = variant >= 100 ? 128 : 256, nc = (variant % 100) / 10, mb = variant % 10;
+#define LBM_T3(CM, MB, NP) if constexpr (NP * Q <= 52) if (cm == CM && mb == MB && nc == (NP == 1 ? 0 : (NP == 2 ? 1 : 2))) { launch_step_cfg<CM, T, true, MB, NP>(p, step, threads, s); return; }
+#define LBM_T2(CM, MB) LBM_T3(CM, MB, 1) LBM_T3(CM, MB, 2) LBM_T3(CM, MB, 4)
+#define LBM_T1(CM) LBM_T2(CM, 1) LBM_T2(CM, 2) LBM_T2(CM, 3) LBM_T2(CM, 4) LBM_T2(CM, 5) LBM_T2(CM, 6) LBM_T2(CM, 8)
+        LBM_T1(LBM_SRT) LBM_T1(LBM_TRT) LBM_T1(LBM_MRT)
+    }
 #endif
-#define LBM_LAUNCH(CM)                                                                       \
-    if (pull) k_step<CM, T, true, DEFAULT_MINB><<<grid, block, 0, s>>>(p, step);             \
-    else k_step<CM, T, false, DEFAULT_MINB><<<grid, block, 0, s>>>(p, step);
+#define LBM_LAUNCH(CM)                                                                                            \
+    {                                                                                                             \
+        constexpr StepCfg c = step_cfg<CM, T>();                                                                  \
+        if (pull) launch_step_cfg<CM, T, true, c.minb, c.npt>(p, step, c.threads, s);                             \
+        else launch_step_cfg<CM, T, false, c.minb, c.npt>(p, step, c.threads, s);                                 \
+    }
     switch (cm) {
     case LBM_SRT: LBM_LAUNCH(LBM_SRT) break;
     case LBM_TRT: LBM_LAUNCH(LBM_TRT) break;

@@ -151,6 +151,11 @@ static KParams<T> make_params(const lbm_ctx *c, int src, int dst) {
     p.aux = nullptr;
     p.pitch = c->pitch;
     p.plane = c->plane;
+    for (int i = 0; i < c->li.Q; ++i) {
+        p.srcn[i] = p.src + (long long)i * c->plane;
+        p.srcp[i] = p.srcn[i] - (long long)c->li.cy[i] * c->pitch - c->li.cx[i];
+        p.dstp[i] = p.dst + (long long)i * c->plane;
+    }
     p.nx = c->desc.nx;
     p.nyl = c->nyl;
     p.y0g = c->y0;
@@ -443,6 +448,11 @@ int lbm_create(const lbm_desc *d, lbm_ctx **out) {
     c->gy = li.H;
     c->pitch = ((long long)d->nx + 2 * c->gx + align - 1) / align * align;
     c->plane = c->pitch * (c->nyl + 2 * c->gy);
+    if (c->plane >= (1LL << 31)) {
+        const long long pl = c->plane;
+        delete c;
+        return fail(LBM_ERR_INVALID, "slab of %lld elements per population exceeds the 2^31 node-index limit", pl);
+    }
     c->up = (d->rank + 1) % d->world;
     c->down = (d->rank + d->world - 1) % d->world;
 
@@ -495,19 +505,24 @@ static int refresh_ghosts(lbm_ctx *c, int b) {
     return 0;
 }
 
-static int upload_buffer(lbm_ctx *c, int b, const double *f) {
+// host rows [y0, y0+ny) of the local slab ([q][ny][nx]) -> device buffer b
+static int upload_buffer(lbm_ctx *c, int b, const double *f, int y0 = 0, int ny = -1) {
     const int nx = c->desc.nx, Q = c->li.Q;
+    if (ny < 0) ny = c->nyl;
+    if (ny == 0) return 0;
     if (is64(c)) {
-        double *o = origin<double>(c, b);
+        double *o = origin<double>(c, b) + (size_t)y0 * c->pitch;
         for (int i = 0; i < Q; ++i)
-            CU(cudaMemcpy2DAsync(o + (size_t)i * c->plane, c->pitch * 8, f + (size_t)i * c->nyl * nx, (size_t)nx * 8,
-                                 (size_t)nx * 8, c->nyl, cudaMemcpyHostToDevice, c->stream));
+            CU(cudaMemcpy2DAsync(o + (size_t)i * c->plane, c->pitch * 8, f + (size_t)i * ny * nx, (size_t)nx * 8,
+                                 (size_t)nx * 8, ny, cudaMemcpyHostToDevice, c->stream));
     } else {
         double *stage = nullptr;
-        CU(cudaMalloc(&stage, (size_t)c->nyl * nx * 8));
+        CU(cudaMalloc(&stage, (size_t)ny * nx * 8));
         KParams<float> p = make_params<float>(c, b, b);
+        p.dst += (size_t)y0 * c->pitch;
+        p.nyl = ny;
         for (int i = 0; i < Q; ++i) {
-            CU(cudaMemcpyAsync(stage, f + (size_t)i * c->nyl * nx, (size_t)c->nyl * nx * 8, cudaMemcpyHostToDevice, c->stream));
+            CU(cudaMemcpyAsync(stage, f + (size_t)i * ny * nx, (size_t)ny * nx * 8, cudaMemcpyHostToDevice, c->stream));
             c->ops->import32(p, stage, i, c->stream);
             c->launches += 1;
         }
@@ -549,21 +564,25 @@ int lbm_upload_f_collision(lbm_ctx *c, const double *f) {
     return 0;
 }
 
-static int download_buffer(lbm_ctx *c, int b, double *f) {
+static int download_buffer(lbm_ctx *c, int b, double *f, int y0 = 0, int ny = -1) {
     const int nx = c->desc.nx, Q = c->li.Q;
+    if (ny < 0) ny = c->nyl;
+    if (ny == 0) return 0;
     if (is64(c)) {
-        const double *o = origin<double>(c, b);
+        const double *o = origin<double>(c, b) + (size_t)y0 * c->pitch;
         for (int i = 0; i < Q; ++i)
-            CU(cudaMemcpy2DAsync(f + (size_t)i * c->nyl * nx, (size_t)nx * 8, o + (size_t)i * c->plane, c->pitch * 8,
-                                 (size_t)nx * 8, c->nyl, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaMemcpy2DAsync(f + (size_t)i * ny * nx, (size_t)nx * 8, o + (size_t)i * c->plane, c->pitch * 8,
+                                 (size_t)nx * 8, ny, cudaMemcpyDeviceToHost, c->stream));
     } else {
         double *stage = nullptr;
-        CU(cudaMalloc(&stage, (size_t)c->nyl * nx * 8));
+        CU(cudaMalloc(&stage, (size_t)ny * nx * 8));
         KParams<float> p = make_params<float>(c, b, b);
+        p.src += (size_t)y0 * c->pitch;
+        p.nyl = ny;
         for (int i = 0; i < Q; ++i) {
             c->ops->export32(p, stage, i, c->stream);
             c->launches += 1;
-            CU(cudaMemcpyAsync(f + (size_t)i * c->nyl * nx, stage, (size_t)c->nyl * nx * 8, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaMemcpyAsync(f + (size_t)i * ny * nx, stage, (size_t)ny * nx * 8, cudaMemcpyDeviceToHost, c->stream));
         }
         CU(cudaStreamSynchronize(c->stream));
         CU(cudaFree(stage));
@@ -590,6 +609,37 @@ int lbm_download_f_collision(lbm_ctx *c, double *f) {
     }
     if (!c->have_coll) return fail(LBM_ERR_STATE, "no f_collision: collide! has not run since the last upload");
     return download_buffer(c, 1 - c->cur, f);
+}
+
+static int check_rows(lbm_ctx *c, int y0, int ny) {
+    if (y0 < 0 || ny < 0 || y0 + ny > c->nyl) return fail(LBM_ERR_INVALID, "rows [%d, %d) outside the local slab of %d rows", y0, y0 + ny, c->nyl);
+    return 0;
+}
+
+int lbm_upload_f_rows(lbm_ctx *c, int32_t y0, int32_t ny, const double *f_rows) {
+    if (!c || !f_rows) return fail(LBM_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(c->desc.device));
+    int rc = check_rows(c, y0, ny);
+    if (rc) return rc;
+    rc = materialize(c);
+    if (rc) return rc;
+    rc = wait_comm(c);
+    if (rc) return rc;
+    rc = upload_buffer(c, c->cur, f_rows, y0, ny);
+    if (rc) return rc;
+    c->have_coll = false;
+    c->resume_ok = false;
+    return 0;
+}
+
+int lbm_download_f_rows(lbm_ctx *c, int32_t y0, int32_t ny, double *f_rows) {
+    if (!c || !f_rows) return fail(LBM_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(c->desc.device));
+    int rc = check_rows(c, y0, ny);
+    if (rc) return rc;
+    rc = materialize(c);
+    if (rc) return rc;
+    return download_buffer(c, c->cur, f_rows, y0, ny);
 }
 
 static void free_force(lbm_ctx *c) {

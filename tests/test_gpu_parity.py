@@ -441,3 +441,26 @@ def test_f32_config_c2_crop_100_steps(oracle):
             assert rel_max(mo["ux"].T, ux) < tol and rel_max(mo["uy"].T, uy) < tol, (dtype, arith)
             if dtype == "f64" and arith == "exact":
                 assert np.array_equal(got, want)
+
+
+def test_row_chunked_upload_download(oracle):
+    """lbm_upload_f_rows / lbm_download_f_rows == the whole-array calls (both dtypes)."""
+    O = oracle
+    qo = O.L.D2Q13()
+    nx, ny = 20, 17
+    f0 = random_populations(qo, nx, ny, seed=31)
+    host = to_host_layout(f0)
+    for dtype in (_abi.F64, _abi.F32):
+        with _ctx("D2Q13", _abi.TRT, [0.8, 1.1], [], nx, ny, _abi.ARITH_EXACT, dtype=dtype) as a, \
+                _ctx("D2Q13", _abi.TRT, [0.8, 1.1], [], nx, ny, _abi.ARITH_EXACT, dtype=dtype) as b:
+            a.upload_f(host)
+            for y0, n in ((0, 5), (5, 1), (6, 11)):
+                b.upload_f_rows(y0, host[:, y0:y0 + n, :])
+            a.step(0, 4)
+            b.step(0, 4)
+            fa = a.download_f()
+            assert np.array_equal(fa, b.download_f())
+            parts = [b.download_f_rows(y0, n) for y0, n in ((0, 9), (9, 8))]
+            assert np.array_equal(np.concatenate(parts, axis=1), fa)
+            with pytest.raises(lbm.LbmError):
+                b.download_f_rows(10, 8)
