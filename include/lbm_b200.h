@@ -118,6 +118,12 @@ int lbm_download_f(lbm_ctx *ctx, double *f);
  * host initialise / read grids larger than its own memory chunk by chunk (32768^2: 77 GB). */
 int lbm_upload_f_rows(lbm_ctx *ctx, int32_t y0, int32_t ny, const double *f_rows);
 int lbm_download_f_rows(lbm_ctx *ctx, int32_t y0, int32_t ny, double *f_rows);
+/* Device-side initialize(): rows [y0, y0+ny) of f_stream := hermite_based_equilibrium!(q, rho, u, T) per node
+ * (src/velocity_distribution_function/hermite.jl:10-33, called by initial_conditions/analytical_equilibrium.jl:8-17,
+ * constant_density.jl:10-20 through problems/problems.jl:121-128), from host Float64 fields [ny][nx] in lattice units.
+ * Moves 4 instead of Q values per node over PCIe and keeps the Hermite evaluation off the host. */
+int lbm_init_equilibrium_rows(lbm_ctx *ctx, int32_t y0, int32_t ny, const double *rho, const double *ux,
+                              const double *uy, const double *T);
 int lbm_download_f_collision(lbm_ctx *ctx, double *f);
 
 /* The force closure `collision_model.force(x_idx, y_idx, time)` (srt.jl:10-12,52; trt.jl:17-18,77;

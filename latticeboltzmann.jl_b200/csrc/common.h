@@ -91,6 +91,9 @@ struct Ops {
     // host f64 [q][nyl][nx] staging <-> device storage conversion (f32 stores f - w)
     void (*import32)(const KParams<float> &p, const double *staging, int plane_idx, cudaStream_t s);
     void (*export32)(const KParams<float> &p, double *staging, int plane_idx, cudaStream_t s);
+    // device-side hermite_based_equilibrium! from host-provided (rho, ux, uy, T) rows
+    void (*init_eq64)(const KParams<double> &p, const double *rho, const double *ux, const double *uy, const double *T, cudaStream_t s);
+    void (*init_eq32)(const KParams<float> &p, const double *rho, const double *ux, const double *uy, const double *T, cudaStream_t s);
     int (*init_constants)();  // uploads the __constant__ lattice tables on the current device
 };
 

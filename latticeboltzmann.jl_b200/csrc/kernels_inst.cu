@@ -653,6 +653,64 @@ __global__ void k_reduce_final(const ReduceArgs ra) {
     }
 }
 
+// K7: device-side initialisation.  f_i = hermite_based_equilibrium!(q, rho, u, T)
+// (velocity_distribution_function/hermite.jl:10-33) from per-node fields [ny][nx] (Float64):
+//   f_i = w_i (rho + sum_{n=1..N} <a_eq^(n), H_n(c_i)> / (n! (1/css)^n)),  a_eq = equilibrium_coefficient(Val{n}, q, rho, u, T)
+// including the (T - 1) terms and the Val{4} delta-index quirk (hermite.jl:69,71), evaluated over the full
+// (non-symmetric) index set.  Writes rows [0, p.nyl) of dst (the caller offsets dst / sets nyl).
+template <typename T>
+__global__ void __launch_bounds__(256) k_init_eq(const __grid_constant__ KParams<T> p, const double *rho_, const double *ux_,
+                                                 const double *uy_, const double *T_) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= p.nx) return;
+    const LatConst<double> &c = c_lat64;
+    for (int y = blockIdx.y * blockDim.y + threadIdx.y; y < p.nyl; y += gridDim.y * blockDim.y) {
+        const long long n = (long long)y * p.nx + x;
+        const double rho = rho_[n], u[2] = {ux_[n], uy_[n]}, Tm1 = T_[n] - 1;
+        const double cs = c.cs_inv;
+        // a_eq^(n)[t], t = bit string of the indices (bit k = k-th index)
+        double a2[4], a3[8], a4[16];
+        auto d = [](int a, int b) { return a == b ? 1.0 : 0.0; };
+        for (int t = 0; t < 4; ++t) {
+            const int a = t & 1, b = (t >> 1) & 1;
+            a2[t] = rho * (u[a] * u[b] + cs * Tm1 * d(a, b));
+        }
+        for (int t = 0; t < 8; ++t) {
+            const int a = t & 1, b = (t >> 1) & 1, e = (t >> 2) & 1;
+            a3[t] = rho * (u[a] * u[b] * u[e] + cs * Tm1 * (u[a] * d(b, e) + u[b] * d(a, e) + u[e] * d(a, b)));
+        }
+        for (int t = 0; t < 16; ++t) {
+            const int a = t & 1, b = (t >> 1) & 1, e = (t >> 2) & 1, g = (t >> 3) & 1;
+            a4[t] = rho * (u[a] * u[b] * u[e] * u[g]
+                           + cs * Tm1 * (u[a] * u[b] * d(e, g) + u[a] * u[e] * d(b, g) + u[a] * u[g] * d(b, g)
+                                         + u[b] * u[e] * d(a, g) + u[b] * u[g] * d(a, g) + u[e] * u[g] * d(a, b))
+                           + cs * cs * Tm1 * Tm1 * (d(a, b) * d(e, g) + d(a, e) * d(b, g) + d(a, g) * d(b, e)));
+        }
+        static_for<0, Q>([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            double s = (rho * u[0] * L::cx(i) + rho * u[1] * L::cy(i)) / cs;
+            if constexpr (NH >= 2) {
+                double dot = 0;
+                for (int t = 0; t < 4; ++t) dot += a2[t] * c.H2[i][__popc(t)];
+                s += dot / (2 * cs * cs);
+            }
+            if constexpr (NH >= 3) {
+                double dot = 0;
+                for (int t = 0; t < 8; ++t) dot += a3[t] * c.H3[i][__popc(t)];
+                s += dot / (6 * cs * cs * cs);
+            }
+            if constexpr (NH >= 4) {
+                double dot = 0;
+                for (int t = 0; t < 16; ++t) dot += a4[t] * c.H4[i][__popc(t)];
+                s += dot / (24 * cs * cs * cs * cs);
+            }
+            const long long m = i * p.plane + (long long)y * p.pitch + x;
+            if constexpr (Shifted<T>::value) p.dst[m] = (T)(c.w[i] * ((rho - 1) + s));
+            else p.dst[m] = (T)(c.w[i] * (rho + s));
+        });
+    }
+}
+
 // Float32 storage <-> host Float64 planes: g = (float)(f - w), f = (double)g + w
 __global__ void __launch_bounds__(256) k_import32(const __grid_constant__ KParams<float> p, const double *stage, int i) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -684,6 +742,8 @@ static inline dim3 grid_for(const KParams<T> &p, const dim3 &block, int rows, in
     return dim3((cols + block.x - 1) / block.x, gy, 1);
 }
 
+#include "packed_f32.cuh"
+
 // Launch configuration of the fused kernel per <collision model, dtype>: {MINB, NPT, CTA threads},
 // chosen from tools/sweep.py runs on B200 (profiles/r01_sweep_summary.md).
 struct StepCfg { int minb, npt, threads; };
@@ -709,9 +769,25 @@ static void launch_step_cfg(const KParams<T> &p, long long step, int threads, cu
     k_step<CM, T, PULL, MINB, NPT><<<grid, block, 0, s>>>(p, step);
 }
 
+constexpr int X2_MINB = (Q <= 13) ? 4 : ((Q <= 17) ? 3 : 2);
+
 template <typename T>
 static void launch_step(int cm, bool pull, const KParams<T> &p, long long step, int variant, cudaStream_t s) {
     if (p.nrows <= 0) return;
+    if constexpr (LBM_FAST && std::is_same<T, float>::value) {
+        // Float32 fast mode: packed two-nodes-per-thread kernel (variant 99 forces the scalar one)
+        // (measured faster for Q <= 13; the wide lattices run out of registers with 64-bit pairs -- variant 98 forces it)
+        if (((Q <= 13 && variant != 99) || variant == 98) && cm != LBM_MRT && p.nx % 2 == 0 && p.nx >= 2) {
+            if (cm == LBM_SRT) {
+                if (pull) launch_step_x2<LBM_SRT, true, X2_MINB>(p, step, s);
+                else launch_step_x2<LBM_SRT, false, X2_MINB>(p, step, s);
+            } else {
+                if (pull) launch_step_x2<LBM_TRT, true, X2_MINB>(p, step, s);
+                else launch_step_x2<LBM_TRT, false, X2_MINB>(p, step, s);
+            }
+            return;
+        }
+    }
 #ifdef LBM_TUNE
     // variant = MINB + 10 * log2(NPT) + 100 * (128-thread CTAs); 0 = production configuration
     if (pull && variant > 0) {
@@ -783,6 +859,12 @@ static void launch_export32(const KParams<float> &p, double *stage, int i, cudaS
     k_export32<<<grid_for(p, block, p.nyl, p.nx), block, 0, s>>>(p, stage, i);
 }
 
+template <typename T>
+static void launch_init_eq(const KParams<T> &p, const double *rho, const double *ux, const double *uy, const double *Tm, cudaStream_t s) {
+    dim3 block; pick_block(p.nx, block);
+    k_init_eq<T><<<grid_for(p, block, p.nyl, p.nx), block, 0, s>>>(p, rho, ux, uy, Tm);
+}
+
 static const Ops ops = {
     LBM_LATTICE, LBM_FAST,
     &launch_step<double>, &launch_step<float>,
@@ -792,6 +874,7 @@ static const Ops ops = {
     &launch_moments<double>, &launch_moments<float>,
     &launch_reduce<double>, &launch_reduce<float>,
     &launch_import32, &launch_export32,
+    &launch_init_eq<double>, &launch_init_eq<float>,
     &init_constants,
 };
 

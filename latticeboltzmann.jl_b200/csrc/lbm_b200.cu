@@ -115,8 +115,8 @@ struct lbm_ctx {
     int state = ST_STREAM;
     bool have_coll = false;  // buf[1-cur] holds f_collision matching f_stream in buf[cur]
     bool resume_ok = false;  // ... and its ghosts/halos are valid, so the next step may pull from it
-    cudaStream_t stream = nullptr, comm_stream = nullptr;
-    cudaEvent_t ev_b = nullptr, ev_c = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_u0 = nullptr, ev_u1 = nullptr;
+    cudaStream_t stream = nullptr, comm_stream = nullptr, bstream = nullptr;  // bstream: boundary-row kernels
+    cudaEvent_t ev_b = nullptr, ev_c = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_u0 = nullptr, ev_u1 = nullptr, ev_fork = nullptr;
     bool comm_pending = false;
     // force
     int force_mode = 0;
@@ -262,9 +262,10 @@ static int post_exchange(lbm_ctx *c, int b) {
 // kernel sequencing
 // ----------------------------------------------------------------------------------------------
 template <typename T>
-static void run_step(lbm_ctx *c, bool pull, const KParams<T> &p, long long step) {
-    if (std::is_same<T, double>::value) c->ops->step64(c->desc.collision, pull, reinterpret_cast<const KParams<double> &>(p), step, c->opt_variant, c->stream);
-    else c->ops->step32(c->desc.collision, pull, reinterpret_cast<const KParams<float> &>(p), step, c->opt_variant, c->stream);
+static void run_step(lbm_ctx *c, bool pull, const KParams<T> &p, long long step, cudaStream_t s = nullptr) {
+    if (!s) s = c->stream;
+    if (std::is_same<T, double>::value) c->ops->step64(c->desc.collision, pull, reinterpret_cast<const KParams<double> &>(p), step, c->opt_variant, s);
+    else c->ops->step32(c->desc.collision, pull, reinterpret_cast<const KParams<float> &>(p), step, c->opt_variant, s);
     c->launches += 1;
 }
 
@@ -289,16 +290,29 @@ static int do_fused(lbm_ctx *c, int src, int dst, long long step) {
         if (rc) return rc;
         run_step<T>(c, true, p, step);
     } else {
-        // interior rows need no halo -> launch them first, then wait for the previous exchange and
-        // do the 2H boundary rows; their exchange then overlaps the next step's interior.
+        // The 2H boundary rows are the only ones that read halos and the only ones the neighbours need.
+        // They run on a high-priority side stream concurrently with the interior kernel:
+        //   main   : [fork] interior(t) ........................ [join ev_b]
+        //   bstream: wait fork, wait exchange(t-1); boundary(t); record ev_b
+        //   comm   : wait ev_b; NCCL send/recv of the boundary rows (overlaps interior(t+1)); record ev_c
+        CU(cudaEventRecord(c->ev_fork, c->stream));  // everything of step t-1 (incl. its boundary rows) is done
+        CU(cudaStreamWaitEvent(c->bstream, c->ev_fork, 0));
+        if (c->comm_pending) CU(cudaStreamWaitEvent(c->bstream, c->ev_c, 0));
+        KParams<T> pb = p;
+        pb.row_a0 = 0; pb.row_an = H; pb.row_b0 = c->nyl - H; pb.nrows = 2 * H;
+        run_step<T>(c, true, pb, step, c->bstream);
+        CU(cudaEventRecord(c->ev_b, c->bstream));
         KParams<T> pi = p;
         pi.row_a0 = H; pi.row_an = c->nyl - 2 * H; pi.nrows = pi.row_an;
         run_step<T>(c, true, pi, step);
-        int rc = wait_comm(c);
+        CU(cudaGetLastError());
+        CU(cudaStreamWaitEvent(c->stream, c->ev_b, 0));  // join
+        CU(cudaStreamWaitEvent(c->comm_stream, c->ev_b, 0));
+        int rc = exchange_halos(c, dst, c->comm_stream);
         if (rc) return rc;
-        KParams<T> pb = p;
-        pb.row_a0 = 0; pb.row_an = H; pb.row_b0 = c->nyl - H; pb.nrows = 2 * H;
-        run_step<T>(c, true, pb, step);
+        CU(cudaEventRecord(c->ev_c, c->comm_stream));
+        c->comm_pending = true;
+        return 0;
     }
     CU(cudaGetLastError());
     return post_exchange(c, dst);
@@ -390,13 +404,15 @@ void lbm_destroy(lbm_ctx *c) {
     cudaSetDevice(c->desc.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
+    if (c->bstream) cudaStreamSynchronize(c->bstream);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     for (void *p : {c->buf[0], c->buf[1], c->field, c->sep_fx, c->sep_fy, (void *)c->partials, (void *)c->red_out, (void *)c->u_old})
         if (p) cudaFree(p);
-    for (cudaEvent_t e : {c->ev_b, c->ev_c, c->ev_t0, c->ev_t1, c->ev_u0, c->ev_u1})
+    for (cudaEvent_t e : {c->ev_b, c->ev_c, c->ev_t0, c->ev_t1, c->ev_u0, c->ev_u1, c->ev_fork})
         if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
+    if (c->bstream) cudaStreamDestroy(c->bstream);
     delete c;
 }
 
@@ -447,7 +463,11 @@ int lbm_create(const lbm_desc *d, lbm_ctx **out) {
     c->gx = d->nx >= 128 ? align : 4;
     c->gy = li.H;
     c->pitch = ((long long)d->nx + 2 * c->gx + align - 1) / align * align;
-    c->plane = c->pitch * (c->nyl + 2 * c->gy);
+    // layout experiments (DRAM channel mapping of the Q concurrently streamed planes)
+    if (const char *e = getenv("LBM_PAD_PITCH")) c->pitch += (long long)atoi(e) * align;
+    long long plane_rows = c->nyl + 2 * c->gy;
+    c->plane = c->pitch * plane_rows;
+    if (const char *e = getenv("LBM_PAD_PLANE")) c->plane += (long long)atoi(e) * align;
     if (c->plane >= (1LL << 31)) {
         const long long pl = c->plane;
         delete c;
@@ -469,6 +489,8 @@ int lbm_create(const lbm_desc *d, lbm_ctx **out) {
     }
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&c->bstream, cudaStreamNonBlocking, -1) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_c, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&c->ev_t0) != cudaSuccess || cudaEventCreate(&c->ev_t1) != cudaSuccess ||
@@ -627,6 +649,48 @@ int lbm_upload_f_rows(lbm_ctx *c, int32_t y0, int32_t ny, const double *f_rows) 
     if (rc) return rc;
     rc = upload_buffer(c, c->cur, f_rows, y0, ny);
     if (rc) return rc;
+    c->have_coll = false;
+    c->resume_ok = false;
+    return 0;
+}
+
+int lbm_init_equilibrium_rows(lbm_ctx *c, int32_t y0, int32_t ny, const double *rho, const double *ux, const double *uy,
+                              const double *T) {
+    if (!c || !rho || !ux || !uy || !T) return fail(LBM_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(c->desc.device));
+    int rc = check_rows(c, y0, ny);
+    if (rc) return rc;
+    if (ny == 0) return 0;
+    rc = materialize(c);
+    if (rc) return rc;
+    rc = wait_comm(c);
+    if (rc) return rc;
+    const size_t N = (size_t)ny * c->desc.nx;
+    double *dev = nullptr;
+    CU(cudaMalloc(&dev, 4 * N * 8));
+    const double *host[4] = {rho, ux, uy, T};
+    cudaError_t e = cudaSuccess;
+    for (int k = 0; k < 4 && e == cudaSuccess; ++k)
+        e = cudaMemcpyAsync(dev + k * N, host[k], N * 8, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        if (is64(c)) {
+            KParams<double> p = make_params<double>(c, c->cur, c->cur);
+            p.dst += (size_t)y0 * c->pitch;
+            p.nyl = ny;
+            c->ops->init_eq64(p, dev, dev + N, dev + 2 * N, dev + 3 * N, c->stream);
+        } else {
+            KParams<float> p = make_params<float>(c, c->cur, c->cur);
+            p.dst += (size_t)y0 * c->pitch;
+            p.nyl = ny;
+            c->ops->init_eq32(p, dev, dev + N, dev + 2 * N, dev + 3 * N, c->stream);
+        }
+        c->launches += 1;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(dev);
+    if (e != cudaSuccess) return fail(LBM_ERR_CUDA, "lbm_init_equilibrium_rows: %s", cudaGetErrorString(e));
+    c->state = ST_STREAM;
     c->have_coll = false;
     c->resume_ok = false;
     return 0;
@@ -794,6 +858,7 @@ int lbm_sync(lbm_ctx *c) {
     if (!c) return fail(LBM_ERR_INVALID, "null context");
     CU(cudaSetDevice(c->desc.device));
     CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->bstream));
     CU(cudaStreamSynchronize(c->comm_stream));
     return 0;
 }

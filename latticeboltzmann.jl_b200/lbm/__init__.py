@@ -12,7 +12,8 @@ from .boundary_conditions import (BoundaryCondition, BounceBack, Direction, East
 from .collision_models import MRT, SRT, TRT, CollisionModel, LatticeForce, TRT_Lambda
 from .initial_conditions import (AnalyticalEquilibrium, AnalyticalEquilibriumAndOffEquilibrium, AnalyticalVelocity,
                                  AnalyticalVelocityAndStress, ConstantDensity, InitializationStrategy,
-                                 IterativeInitializationMeiEtAl, ZeroVelocityInitialCondition, initialize)
+                                 IterativeInitializationMeiEtAl, ZeroVelocityInitialCondition, initialize,
+                                 initialize_on_device)
 from .model import (DeviceState, LatticeBoltzmannModel, apply_, apply_boundary_conditions_, collide_,
                     collide_model_, next_model_, simulate, simulate_model, stream_, stream_model_)
 from .parallel import SlabComm, halo_rows_per_direction, slab_rows

@@ -31,7 +31,7 @@ REDUCE_MEAN_UX, REDUCE_VELOCITY_CHANGE, REDUCE_CONSERVED = 0, 1, 2
 EXPORTS = [
     "lbm_abi_version", "lbm_last_error", "lbm_lattice_info", "lbm_nccl_unique_id", "lbm_create",
     "lbm_destroy", "lbm_local_rows", "lbm_upload_f", "lbm_upload_f_collision", "lbm_download_f",
-    "lbm_upload_f_rows", "lbm_download_f_rows",
+    "lbm_upload_f_rows", "lbm_download_f_rows", "lbm_init_equilibrium_rows",
     "lbm_download_f_collision",
     "lbm_set_force_none", "lbm_set_force_uniform", "lbm_set_force_field", "lbm_set_force_separable",
     "lbm_collide", "lbm_stream", "lbm_apply_bcs", "lbm_step", "lbm_sync", "lbm_moments", "lbm_reduce",
@@ -90,6 +90,7 @@ def lib():
     l.lbm_download_f.argtypes = [vp, vp]
     l.lbm_upload_f_rows.argtypes = [vp, C.c_int32, C.c_int32, vp]
     l.lbm_download_f_rows.argtypes = [vp, C.c_int32, C.c_int32, vp]
+    l.lbm_init_equilibrium_rows.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, vp, vp]
     l.lbm_download_f_collision.argtypes = [vp, vp]
     l.lbm_set_force_none.argtypes = [vp]
     l.lbm_set_force_uniform.argtypes = [vp, C.c_double, C.c_double]
@@ -228,6 +229,12 @@ class Context:
         if f_rows.ndim != 3 or f_rows.shape[0] != self.nx or f_rows.shape[2] != self.Q:
             raise ValueError(f"expected (NX={self.nx}, ny, Q={self.Q})")
         check(lib().lbm_upload_f_rows(self._h, int(y0), f_rows.shape[1], f_rows.ctypes.data))
+
+    def init_equilibrium_rows(self, y0, rho, ux, uy, T):
+        """rows y0.. of f_stream := hermite_based_equilibrium!(q, rho, u, T); fields are (NX, ny) arrays."""
+        ny = np.shape(rho)[1]
+        arrs = [np.asfortranarray(np.broadcast_to(np.asarray(a, dtype=np.float64), (self.nx, ny))) for a in (rho, ux, uy, T)]
+        check(lib().lbm_init_equilibrium_rows(self._h, int(y0), int(ny), *[a.ctypes.data for a in arrs]))
 
     def download_f_rows(self, y0, ny):
         out = np.empty((self.nx, int(ny), self.Q), dtype=np.float64, order="F")

@@ -112,3 +112,27 @@ def initialize(strategy, q, problem, cm=None, rows=None):
     else:
         raise TypeError(f"unknown initialisation strategy {strategy!r}")
     return np.asfortranarray(f, dtype=np.float64)
+
+
+def initialize_on_device(strategy, q, problem, ctx, chunk_nodes=1 << 24):
+    """initialize(strategy, q, problem) evaluated on the device: the host only produces the analytic
+    (rho, u, T) fields, row block by row block; the Hermite-series equilibrium runs in the CUDA library
+    (lbm_init_equilibrium_rows).  Supports the equilibrium-only strategies; returns False otherwise."""
+    if not isinstance(strategy, (ZeroVelocityInitialCondition, AnalyticalEquilibrium, ConstantDensity)):
+        return False
+    rows = max(1, min(ctx.ny_local, chunk_nodes // max(problem.NX, 1)))
+    for off in range(0, ctx.ny_local, rows):
+        n = min(rows, ctx.ny_local - off)
+        X, Y = problem.grid(ctx.y0 + off, n)
+        one = np.ones_like(X)
+        if isinstance(strategy, ZeroVelocityInitialCondition):
+            rho, ux, uy, T = one, 0 * one, 0 * one, one
+        elif isinstance(strategy, ConstantDensity):
+            ux, uy = problem.lattice_velocity(q, X, Y)
+            rho, T = one, one
+        else:
+            rho = problem.lattice_density(q, X, Y)
+            ux, uy = problem.lattice_velocity(q, X, Y)
+            T = problem.lattice_temperature(q, X, Y)
+        ctx.init_equilibrium_rows(off, rho, ux, uy, T)
+    return True

@@ -9,7 +9,7 @@ import numpy as np
 from . import _abi
 from .boundary_conditions import BounceBack, MovingWall
 from .collision_models import MRT, SRT, TRT, CollisionModel, LatticeForce
-from .initial_conditions import default_strategy, initialize
+from .initial_conditions import default_strategy, initialize, initialize_on_device
 from .processing_methods import ProcessingMethod
 
 _DTYPES = {"f64": _abi.F64, "float64": _abi.F64, np.float64: _abi.F64, "f32": _abi.F32, "float32": _abi.F32,
@@ -137,14 +137,14 @@ class LatticeBoltzmannModel:
     ("f64" | "f32"), `arith` ("exact" | "fast"), `comm` (SlabComm for y-slab multi-GPU)."""
 
     def __init__(self, problem, quadrature, collision_model=SRT, initialization_strategy=None, process_method=None,
-                 dtype="f64", arith="exact", comm=None, device=None):
+                 dtype="f64", arith="exact", comm=None, device=None, device_init=False):
         strategy = default_strategy(problem) if initialization_strategy is None else initialization_strategy
         cm = CollisionModel(collision_model, quadrature, problem)
         bcs = problem.boundary_conditions()
         ctx = make_context(quadrature, cm, bcs, problem.NX, problem.NY, dtype, arith, comm, device)
-        f0 = initialize(strategy, quadrature, problem, collision_model, rows=(ctx.y0, ctx.ny_local))
         self._init(ctx, quadrature, cm, bcs, process_method, comm)
-        ctx.upload_f(f0)
+        if not (device_init and initialize_on_device(strategy, quadrature, problem, ctx)):
+            ctx.upload_f(initialize(strategy, quadrature, problem, collision_model, rows=(ctx.y0, ctx.ny_local)))
 
     @classmethod
     def from_fields(cls, f_stream, f_collision, quadrature, collision_model, boundary_conditions, processing_method,

@@ -464,3 +464,24 @@ def test_row_chunked_upload_download(oracle):
             assert np.array_equal(np.concatenate(parts, axis=1), fa)
             with pytest.raises(lbm.LbmError):
                 b.download_f_rows(10, 8)
+
+
+@pytest.mark.parametrize("name", LATTICES)
+def test_device_side_initialisation(name):
+    """lbm_init_equilibrium_rows == initialize(AnalyticalEquilibrium / ConstantDensity / ZeroVelocity)
+    evaluated on the host (hermite_based_equilibrium!, incl. T != 1 and the Val{4} quirk on D2Q37)."""
+    q = getattr(lbm.Quadratures, name)
+    problems = [lbm.TGV(q, 0.8, 1, 12, 10), lbm.DecayingShearFlow.fields(1.0, 0.05, 1 / 6, 12, 10, (2 * np.pi, 2 * np.pi), False, 1.0, 1.0, 1.0, 0.0)]
+    for pr in problems:
+        for strategy in (lbm.AnalyticalEquilibrium(), lbm.ConstantDensity(), lbm.ZeroVelocityInitialCondition()):
+            want = lbm.initialize(strategy, q, pr)
+            for dtype, tol in (("f64", 1e-14), ("f32", 1e-7)):
+                m = lbm.LatticeBoltzmannModel(pr, q, collision_model=lbm.SRT(0.8), initialization_strategy=strategy,
+                                              dtype=dtype, device_init=True)
+                got = m.f_stream
+                m.close()
+                dev = np.abs(want - q.weights).max() + 1e-30
+                if dtype == "f64":
+                    assert np.abs(got - want).max() <= tol * np.abs(want).max(), (name, type(strategy).__name__)
+                else:
+                    assert np.abs(got - want).max() <= 2e-7 * dev + 1e-12, (name, type(strategy).__name__)
