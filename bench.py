@@ -128,6 +128,10 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [v for v in vis.split(",") if v.strip().isdigit()]
+        if device < len(ids):
+            device = int(ids[device])  # nvidia-smi wants the physical index
         self.device, self.rows, self.proc = device, [], None
 
     def start(self):

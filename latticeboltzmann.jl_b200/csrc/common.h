@@ -53,6 +53,7 @@ struct KParams {
     long long sep_t0;
     // boundary conditions
     int nbc;
+    int bc_sides;  // bit d set: some boundary condition faces direction d (lbm_direction) -> only those edges take the BC path
     BCd bc[LBM_MAX_BCS];
 };
 

@@ -146,7 +146,9 @@ __device__ __noinline__ int resolve_bc(const KParams<T> &p, int x1, int y1, int 
 
 template <typename T>
 __device__ __forceinline__ bool near_wall(const KParams<T> &p, int x, int yg) {
-    return p.nbc > 0 && (x < H || x >= p.nx - H || yg < H || yg >= p.nyg - H);
+    const int m = p.bc_sides;
+    return m != 0 && (((m >> LBM_WEST) & 1 && x < H) || ((m >> LBM_EAST) & 1 && x >= p.nx - H) ||
+                      ((m >> LBM_SOUTH) & 1 && yg < H) || ((m >> LBM_NORTH) & 1 && yg >= p.nyg - H));
 }
 
 // f_new[x,y,i] = f_old[x,y,opp(i)] (+ 2 a_1 for a moving wall), a_1 = w_i * css * dot(rho_w u_w, c_i)

@@ -196,6 +196,7 @@ static KParams<T> make_params(const lbm_ctx *c, int src, int dst) {
         d.kind = s.kind; d.dir = s.direction;
         d.x0 = s.x0; d.x1 = s.x1; d.y0 = s.y0; d.y1 = s.y1;
         d.ax = s.rho * s.u[0]; d.ay = s.rho * s.u[1];  // equilibrium_coefficient(Val{1}) hermite.jl:41-43
+        p.bc_sides |= 1 << s.direction;
     }
     return p;
 }
@@ -799,11 +800,11 @@ int lbm_stream(lbm_ctx *c) {
     if (rc) return rc;
     if (is64(c)) {
         KParams<double> p = make_params<double>(c, 1 - c->cur, c->cur);
-        p.nbc = 0;
+        p.nbc = 0; p.bc_sides = 0;
         c->ops->stream64(p, c->stream);
     } else {
         KParams<float> p = make_params<float>(c, 1 - c->cur, c->cur);
-        p.nbc = 0;
+        p.nbc = 0; p.bc_sides = 0;
         c->ops->stream32(p, c->stream);
     }
     c->launches += 1;
