@@ -485,3 +485,77 @@ def test_device_side_initialisation(name):
                     assert np.abs(got - want).max() <= tol * np.abs(want).max(), (name, type(strategy).__name__)
                 else:
                     assert np.abs(got - want).max() <= 2e-7 * dev + 1e-12, (name, type(strategy).__name__)
+
+
+# ---------------------------------------------------------------------------------------------
+# The reference's convergence studies (examples/notebooks/notebook_examples.jl:34-69, shear_wave.ipynb,
+# taylor_green_vortex.ipynb, couette.ipynb) run end to end through the host mirror + CUDA library:
+# the quadratic convergence of the method must survive (north_star), and the error values must equal
+# the oracle's.
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", LATTICES)
+def test_shear_wave_convergence_is_second_order(oracle, name):
+    O = oracle
+    q = getattr(lbm.Quadratures, name)
+    qo = O.L.BY_NAME[name]()
+    tau_lb = 0.8
+    errs, errs_o = [], []
+    scales = [1, 2, 4, 8] if name == "D2Q9" else [1, 2, 4]
+    for scale in scales:
+        nu = tau_lb / (2.0 * q.speed_of_sound_squared)
+        problem = lbm.DecayingShearFlow(nu, scale, static=True)
+        n_steps = round(1.0 / problem.delta_t())
+        pm = lbm.TrackHydrodynamicErrors(problem, False, n_steps, lbm.NoStoppingCriteria())
+        res = lbm.simulate(problem, q, process_method=pm, initialization_strategy=lbm.AnalyticalEquilibrium(), t_end=1.0)
+        errs.append(res.processing_method.df[-1]["error_u"])
+        res.close()
+        if scale <= 2:
+            po = O.DecayingShearFlow(nu, scale, static=True)
+            mo = O.simulate(po, qo, pm=O.TrackHydrodynamicErrors(po, False, n_steps, O.NoStoppingCriteria()), t_end=1.0)
+            errs_o.append(mo.pm.df[-1]["error_u"])
+    for a, b in zip(errs, errs_o):
+        assert abs(a - b) <= 1e-9 * abs(b), (errs, errs_o)
+    slope = np.polyfit(np.log([8.0 * s for s in scales]), np.log(errs), 1)[0]
+    assert slope <= -1.8, (name, errs, slope)
+
+
+@pytest.mark.parametrize("model", ["SRT", "TRT", "MRT"])
+def test_tgv_decay_convergence_is_second_order(model):
+    q = lbm.D2Q9()
+    cm = {"SRT": lbm.SRT, "TRT": lbm.TRT, "MRT": lbm.MRT}[model]
+    errs = []
+    for scale in (1, 2, 4):
+        problem = lbm.TGV(q, 0.8, scale, 8 * scale, 8 * scale)
+        t_end = round(lbm.decay_time(problem))
+        pm = lbm.TrackHydrodynamicErrors(problem, False, t_end, lbm.NoStoppingCriteria())
+        model_ = lbm.LatticeBoltzmannModel(problem, q, collision_model=cm, process_method=pm)
+        lbm.simulate(model_, range(1, t_end + 1))
+        errs.append(pm.df[-1]["error_u"])
+        model_.close()
+    slope = np.polyfit(np.log([1.0, 2.0, 4.0]), np.log(errs), 1)[0]
+    assert slope <= -1.8, (model, errs, slope)
+
+
+@pytest.mark.parametrize("name", ["D2Q9", "D2Q13", "D2Q17", "D2Q21", "D2Q37"])
+def test_couette_moving_wall_steady_state(oracle, name):
+    """couette.ipynb: CouetteFlow (MovingWall North + BounceBack South) run to the stop criterion;
+    same stopping step and same error as the oracle."""
+    O = oracle
+    q = getattr(lbm.Quadratures, name)
+    qo = O.L.BY_NAME[name]()
+    nu = 0.3 / q.speed_of_sound_squared
+    problem = lbm.CouetteFlow(nu, 2)
+    n_steps = 3000
+    pm = lbm.ProcessingMethod(problem, False, n_steps)
+    model = lbm.LatticeBoltzmannModel(problem, q, collision_model=lbm.TRT, process_method=pm,
+                                      initialization_strategy=lbm.ZeroVelocityInitialCondition())
+    lbm.simulate(model, range(0, n_steps + 1))
+    po = O.CouetteFlow(nu, 2)
+    mo = O.make_model(po, qo, "TRT", strategy="ZeroVelocityInitialCondition", pm=O.processing_method(po, False, n_steps))
+    O.simulate_model(mo, range(0, n_steps + 1))
+    got, want = pm.df[-1], mo.pm.df[-1]
+    assert len(pm.df) == len(mo.pm.df)
+    for k in ("error_u", "error_p", "density", "momentum", "kinetic_energy"):
+        assert abs(got[k] - want[k]) <= 1e-9 * abs(want[k]) + 1e-14, (name, k, got[k], want[k])
+    assert rel_max(to_oracle_layout(model.f_stream), mo.f_stream) < 1e-12
+    model.close()
