@@ -172,6 +172,24 @@ typedef enum {
 /* Local (per-rank) partial sums; the host adds ranks. */
 int lbm_reduce(lbm_ctx *ctx, int32_t kind, double *out, int32_t n);
 
+/* TrackHydrodynamicErrors.next! (processing_methods/track_hydrodynamic_errors.jl:114-203) without moving fields
+ * to the host.  The problem's analytic fields density/velocity/pressure/deviatoric_tensor(q, problem, x, y, t)
+ * (src/problems/*.jl) are passed in separable form -- every shipped problem's fields are sums of at most two
+ * products of a function of x and a function of y:
+ *     E(x, y) = c0 + a[0] x[0][x] y[0][y] + a[1] x[1][x] y[1][y]      (x[k] / y[k] == NULL: all ones)
+ * expected[0..7] = rho, u_x, u_y, p, sigma_xx, sigma_xy, sigma_yx, sigma_yy (dimensionless units); x tables have nx
+ * entries, y tables ny_local.  tau_visc = css * lattice_viscosity, u_max = problem.u_max (unit scaling,
+ * problems.jl:110-119).  out[16] (local partial sums): (rho-e)^2, |u-e_u|^2, |e_u|^2, (p-e_p)^2, e_p^2,
+ * (e_sxx-sxx)^2, e_sxx^2, (e_sxy-sxy)^2, e_sxy^2, (e_syy-syy)^2, e_syy^2, (e_syx-syx)^2, e_syx^2, rho, rho(ux+uy),
+ * rho(ux^2+uy^2). */
+typedef struct {
+    double c0;
+    double a[2];
+    const double *x[2];
+    const double *y[2];
+} lbm_sep_field;
+int lbm_reduce_errors(lbm_ctx *ctx, double tau_visc, double u_max, const lbm_sep_field expected[8], double out[16]);
+
 /* Introspection used by bench.py / tests. */
 int64_t lbm_kernel_launches(const lbm_ctx *ctx); /* kernels launched by this context so far */
 int lbm_last_step_ms(lbm_ctx *ctx, float *ms);    /* CUDA-event time of the last lbm_step batch */

@@ -70,6 +70,20 @@ struct ReduceArgs {
     int nblocks;
 };
 
+// Expected (analytic) fields for the on-device error norms, in separable form
+//   E_f(x, y) = c0[f] + a[f][0] X[f][0](x) Y[f][0](y) + a[f][1] X[f][1](x) Y[f][1](y)
+// f = rho, ux, uy, p, sxx, sxy, syx, syy.  tab holds, per field and term, X (nx values) then Y (nyl values).
+struct ErrorArgs {
+    double c0[8];
+    double a[8][2];
+    const double *tab;   // [8][2][nx + nyl]
+    double tau_visc;     // css * lattice_viscosity
+    double u_max;        // dimensionless_velocity / dimensionless_stress scaling
+    double *partials;    // [nblocks][16]
+    double *out;         // [16] device
+    int nblocks;
+};
+
 // Launchers exported by one kernels_inst.cu instance.
 struct Ops {
     int lattice, arith;
@@ -89,6 +103,8 @@ struct Ops {
     void (*moments32)(bool pull, const KParams<float> &p, const MomentsOut &m, cudaStream_t s);
     void (*reduce64)(bool pull, const KParams<double> &p, const ReduceArgs &r, cudaStream_t s);
     void (*reduce32)(bool pull, const KParams<float> &p, const ReduceArgs &r, cudaStream_t s);
+    void (*errors64)(bool pull, const KParams<double> &p, const ErrorArgs &e, cudaStream_t s);
+    void (*errors32)(bool pull, const KParams<float> &p, const ErrorArgs &e, cudaStream_t s);
     // host f64 [q][nyl][nx] staging <-> device storage conversion (f32 stores f - w)
     void (*import32)(const KParams<float> &p, const double *staging, int plane_idx, cudaStream_t s);
     void (*export32)(const KParams<float> &p, double *staging, int plane_idx, cudaStream_t s);

@@ -646,6 +646,74 @@ __global__ void __launch_bounds__(256) k_reduce(const __grid_constant__ KParams<
     }
 }
 
+// TrackHydrodynamicErrors.next! (track_hydrodynamic_errors.jl:114-203) entirely on the device: per node
+// rho, u, p = tr(P)/D, sigma as in k_moments, scaled to dimensionless units, compared with the problem's
+// analytic fields given in separable form; 16 sums, deterministic two-stage reduction.
+//   0 (rho-e)^2  1 |u-e|^2  2 |e_u|^2  3 (p-e)^2  4 e_p^2  5 (e_sxx-sxx)^2  6 e_sxx^2  7 (e_sxy-sxy)^2  8 e_sxy^2
+//   9 (e_syy-syy)^2  10 e_syy^2  11 (e_syx-syx)^2  12 e_syx^2  13 rho  14 rho (ux+uy)  15 rho (ux^2+uy^2)
+template <typename T, bool PULL>
+__global__ void __launch_bounds__(256) k_errors(const __grid_constant__ KParams<T> p, const __grid_constant__ ErrorArgs ea) {
+    double acc[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc[k] = 0;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const int W = p.nx + p.nyl;
+    const double tau = ea.tau_visc, den = 1 + 1 / (2 * tau), fac = 1 / (ea.u_max * ea.u_max);
+    for (int y = blockIdx.y * blockDim.y + threadIdx.y; y < p.nyl; y += gridDim.y * blockDim.y)
+        for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < p.nx; x += gridDim.x * blockDim.x) {
+            double rho, ux, uy, axx, axy, ayy;
+            node_fields<T, PULL>(p, x, y, rho, ux, uy, axx, axy, ayy);
+            const double exx = rho * (ux * ux), exy = rho * (ux * uy), eyy = rho * (uy * uy);
+            const double bxx = (axx + (1 / (2 * tau)) * exx) / den, byy = (ayy + (1 / (2 * tau)) * eyy) / den;
+            const double pr = ((bxx - rho * (ux * ux - 1)) + (byy - rho * (uy * uy - 1))) / 2;
+            double sxx = (axx - exx) / den, sxy = (axy - exy) / den, syy = (ayy - eyy) / den;
+            const double tr = (sxx + syy) / 2;
+            sxx = (sxx - tr) * fac; syy = (syy - tr) * fac; sxy = sxy * fac;
+            const double vx = ux / ea.u_max, vy = uy / ea.u_max;
+            double e[8];
+#pragma unroll
+            for (int f = 0; f < 8; ++f) {
+                const double *t0 = ea.tab + (size_t)(2 * f) * W, *t1 = t0 + W;
+                e[f] = ea.c0[f] + ea.a[f][0] * (__ldg(t0 + x) * __ldg(t0 + p.nx + y)) + ea.a[f][1] * (__ldg(t1 + x) * __ldg(t1 + p.nx + y));
+            }
+            acc[0] += (rho - e[0]) * (rho - e[0]);
+            acc[1] += (vx - e[1]) * (vx - e[1]) + (vy - e[2]) * (vy - e[2]);
+            acc[2] += e[1] * e[1] + e[2] * e[2];
+            acc[3] += (pr - e[3]) * (pr - e[3]);
+            acc[4] += e[3] * e[3];
+            acc[5] += (e[4] - sxx) * (e[4] - sxx); acc[6] += e[4] * e[4];
+            acc[7] += (e[5] - sxy) * (e[5] - sxy); acc[8] += e[5] * e[5];
+            acc[9] += (e[7] - syy) * (e[7] - syy); acc[10] += e[7] * e[7];
+            acc[11] += (e[6] - sxy) * (e[6] - sxy); acc[12] += e[6] * e[6];
+            acc[13] += rho; acc[14] += rho * (vx + vy); acc[15] += rho * (vx * vx + vy * vy);
+        }
+    __shared__ double sm[16][8];
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        double v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) sm[k][warp] = v;
+    }
+    __syncthreads();
+    if (tid < 16) {
+        const int nw = (blockDim.x * blockDim.y + 31) >> 5;
+        double v = 0;
+        for (int w = 0; w < nw; ++w) v += sm[tid][w];
+        ea.partials[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 + tid] = v;
+    }
+}
+
+__global__ void k_errors_final(const ErrorArgs ea) {
+    const int k = threadIdx.x;
+    if (k < 16) {
+        double v = 0;
+        for (int b = 0; b < ea.nblocks; ++b) v += ea.partials[(size_t)b * 16 + k];
+        ea.out[k] = v;
+    }
+}
+
 __global__ void k_reduce_final(const ReduceArgs ra) {
     const int k = threadIdx.x;
     if (k < 4) {
@@ -852,6 +920,19 @@ static void launch_reduce(bool pull, const KParams<T> &p, const ReduceArgs &r, c
     k_reduce_final<<<1, 32, 0, s>>>(ra);
 }
 
+template <typename T>
+static void launch_errors(bool pull, const KParams<T> &p, const ErrorArgs &e, cudaStream_t s) {
+    dim3 block; pick_block(p.nx, block);
+    dim3 grid = grid_for(p, block, p.nyl, p.nx);
+    while ((long long)grid.x * grid.y > e.nblocks && grid.y > 1) grid.y = (grid.y + 1) / 2;
+    while ((long long)grid.x * grid.y > e.nblocks && grid.x > 1) grid.x = (grid.x + 1) / 2;
+    ErrorArgs ea = e;
+    ea.nblocks = grid.x * grid.y;
+    if (pull) k_errors<T, true><<<grid, block, 0, s>>>(p, ea);
+    else k_errors<T, false><<<grid, block, 0, s>>>(p, ea);
+    k_errors_final<<<1, 32, 0, s>>>(ea);
+}
+
 static void launch_import32(const KParams<float> &p, const double *stage, int i, cudaStream_t s) {
     dim3 block; pick_block(p.nx, block);
     k_import32<<<grid_for(p, block, p.nyl, p.nx), block, 0, s>>>(p, stage, i);
@@ -875,6 +956,7 @@ static const Ops ops = {
     &launch_ghosts<double>, &launch_ghosts<float>,
     &launch_moments<double>, &launch_moments<float>,
     &launch_reduce<double>, &launch_reduce<float>,
+    &launch_errors<double>, &launch_errors<float>,
     &launch_import32, &launch_export32,
     &launch_init_eq<double>, &launch_init_eq<float>,
     &init_constants,

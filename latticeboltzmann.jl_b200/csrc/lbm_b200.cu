@@ -930,6 +930,51 @@ int lbm_moments(lbm_ctx *c, double tau_visc, double *rho, double *ux, double *uy
     return 0;
 }
 
+int lbm_reduce_errors(lbm_ctx *c, double tau_visc, double u_max, const lbm_sep_field *expected, double *out) {
+    if (!c || !expected || !out) return fail(LBM_ERR_INVALID, "null argument");
+    if (!(tau_visc > 0) || !(u_max > 0)) return fail(LBM_ERR_INVALID, "tau_visc %g, u_max %g", tau_visc, u_max);
+    CU(cudaSetDevice(c->desc.device));
+    int rc = wait_comm(c);
+    if (rc) return rc;
+    const int nx = c->desc.nx, nyl = c->nyl, W = nx + nyl;
+    std::vector<double> tab((size_t)16 * W, 1.0);
+    ErrorArgs ea;
+    memset(&ea, 0, sizeof(ea));
+    for (int f = 0; f < 8; ++f) {
+        ea.c0[f] = expected[f].c0;
+        for (int k = 0; k < 2; ++k) {
+            ea.a[f][k] = expected[f].a[k];
+            double *t = tab.data() + (size_t)(2 * f + k) * W;
+            if (expected[f].x[k]) memcpy(t, expected[f].x[k], (size_t)nx * 8);
+            if (expected[f].y[k]) memcpy(t + nx, expected[f].y[k], (size_t)nyl * 8);
+        }
+    }
+    double *dev = nullptr;
+    const int nblocks = 1024;
+    CU(cudaMalloc(&dev, (tab.size() + (size_t)nblocks * 16 + 16) * 8));
+    cudaError_t e = cudaMemcpyAsync(dev, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, c->stream);
+    ea.tab = dev;
+    ea.partials = dev + tab.size();
+    ea.out = ea.partials + (size_t)nblocks * 16;
+    ea.nblocks = nblocks;
+    ea.tau_visc = tau_visc;
+    ea.u_max = u_max;
+    double h[16];
+    if (e == cudaSuccess) {
+        const bool pull = c->state == ST_COLLIDED;
+        if (is64(c)) c->ops->errors64(pull, make_params<double>(c, c->cur, c->cur), ea, c->stream);
+        else c->ops->errors32(pull, make_params<float>(c, c->cur, c->cur), ea, c->stream);
+        c->launches += 2;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, ea.out, sizeof(h), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(dev);
+    if (e != cudaSuccess) return fail(LBM_ERR_CUDA, "lbm_reduce_errors: %s", cudaGetErrorString(e));
+    memcpy(out, h, sizeof(h));
+    return 0;
+}
+
 int lbm_reduce(lbm_ctx *c, int32_t kind, double *out, int32_t n) {
     if (!c || !out || n < 1) return fail(LBM_ERR_INVALID, "bad argument");
     if (kind < LBM_REDUCE_MEAN_UX || kind > LBM_REDUCE_CONSERVED) return fail(LBM_ERR_INVALID, "reduce kind %d", kind);

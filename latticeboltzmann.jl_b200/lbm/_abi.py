@@ -35,6 +35,7 @@ EXPORTS = [
     "lbm_download_f_collision",
     "lbm_set_force_none", "lbm_set_force_uniform", "lbm_set_force_field", "lbm_set_force_separable",
     "lbm_collide", "lbm_stream", "lbm_apply_bcs", "lbm_step", "lbm_sync", "lbm_moments", "lbm_reduce",
+    "lbm_reduce_errors",
     "lbm_kernel_launches", "lbm_last_step_ms", "lbm_timer_start", "lbm_timer_stop", "lbm_set_option",
 ]
 
@@ -49,6 +50,10 @@ class lbm_bc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("direction", C.c_int32),
                 ("x0", C.c_int32), ("x1", C.c_int32), ("y0", C.c_int32), ("y1", C.c_int32),
                 ("u", C.c_double * 2), ("rho", C.c_double), ("T", C.c_double)]
+
+
+class lbm_sep_field(C.Structure):
+    _fields_ = [("c0", C.c_double), ("a", C.c_double * 2), ("x", C.c_void_p * 2), ("y", C.c_void_p * 2)]
 
 
 class lbm_desc(C.Structure):
@@ -103,6 +108,7 @@ def lib():
     l.lbm_sync.argtypes = [vp]
     l.lbm_moments.argtypes = [vp, C.c_double] + [vp] * 8
     l.lbm_reduce.argtypes = [vp, C.c_int32, dp, C.c_int32]
+    l.lbm_reduce_errors.argtypes = [vp, C.c_double, C.c_double, C.POINTER(lbm_sep_field), dp]
     l.lbm_kernel_launches.argtypes = [vp]
     l.lbm_kernel_launches.restype = C.c_int64
     l.lbm_last_step_ms.argtypes = [vp, C.POINTER(C.c_float)]
@@ -299,6 +305,28 @@ class Context:
         buf = (C.c_double * 4)()
         check(lib().lbm_reduce(self._h, int(kind), buf, 4))
         return np.array(buf[:])
+
+    def reduce_errors(self, tau_visc, u_max, expected):
+        """expected: 8 tuples (c0, [(a, X or None, Y or None), ...up to 2 terms]) for
+        rho, ux, uy, p, sxx, sxy, syx, syy; X has NX entries, Y has NY_local.  Returns the 16 local sums."""
+        arr = (lbm_sep_field * 8)()
+        keep = []
+        for f, (c0, terms) in enumerate(expected):
+            arr[f].c0 = float(c0)
+            if len(terms) > 2:
+                raise ValueError("at most two separable terms per field")
+            for k, (a, X, Y) in enumerate(terms):
+                arr[f].a[k] = float(a)
+                for name, tab, n in (("x", X, self.nx), ("y", Y, self.ny_local)):
+                    if tab is not None:
+                        t = np.ascontiguousarray(tab, dtype=np.float64)
+                        if t.shape != (n,):
+                            raise ValueError(f"separable table '{name}' must have {n} entries")
+                        keep.append(t)
+                        getattr(arr[f], name)[k] = t.ctypes.data
+        out = (C.c_double * 16)()
+        check(lib().lbm_reduce_errors(self._h, float(tau_visc), float(u_max), arr, out))
+        return np.array(out[:])
 
     # ---- introspection -------------------------------------------------------------------
     @property

@@ -74,6 +74,17 @@ class FluidFlowProblem:
     def boundary_conditions(self):
         return []
 
+    def expected_separable(self, q, t, y0=0, ny=None):
+        """The analytic fields rho, u_x, u_y, p, sigma_xx, sigma_xy, sigma_yx, sigma_yy at time t as
+        sums of <= 2 products X(x) Y(y): [(c0, [(a, X | None, Y | None), ...]), ...] -- the input of the
+        on-device error norms (lbm_reduce_errors).  None: not available for this problem."""
+        return None
+
+    def _xy(self, y0=0, ny=None):
+        xr, yr = self.range()
+        ny = self.NY - y0 if ny is None else ny
+        return xr, yr[y0:y0 + ny]
+
     # --- lattice units (problems.jl:97-106) ------------------------------------------------
     def lattice_density(self, q, x, y, t=0.0):
         return self.density(q, x, y, t)
@@ -190,6 +201,27 @@ class TGV(FluidFlowProblem):
         z = 0.0 * np.asarray(x, dtype=np.float64)
         return z, z
 
+    def expected_separable(self, q, t, y0=0, ny=None):
+        xr, yr = self._xy(y0, ny)
+        kx, ky, td = self._k()
+        X, Y = xr * self.NX, yr * self.NY
+        cs, u0, nu = q.speed_of_sound_squared, self.u_0, self.nu
+        D1, D2 = np.exp(-t / td), np.exp(-2 * t / td)
+        cx, sx, cy, sy = np.cos(kx * X), np.sin(kx * X), np.cos(ky * Y), np.sin(ky * Y)
+        c2x, c2y = np.cos(2 * kx * X), np.cos(2 * ky * Y)
+        K = cs * (u0 ** 2 / 4) * D2
+        s = D1 * u0
+        return [
+            (self.rho_0, [(-self.rho_0 * K * (ky / kx), c2x, None), (-self.rho_0 * K * (kx / ky), None, c2y)]),
+            (0.0, [(-s * np.sqrt(ky / kx), cx, sy)]),
+            (0.0, [(s * np.sqrt(kx / ky), sx, cy)]),
+            (self.rho_0, [(-K * (ky / kx), c2x, None), (-K * (kx / ky), None, c2y)]),
+            (0.0, [(-nu * 2 * s * np.sqrt(ky * kx), sx, sy)]),
+            (0.0, [(-nu * s * (np.sqrt(kx ** 3 / ky) - np.sqrt(ky ** 3 / kx)), cx, cy)]),
+            (0.0, [(-nu * s * (np.sqrt(kx ** 3 / ky) - np.sqrt(ky ** 3 / kx)), cx, cy)]),
+            (0.0, [(nu * 2 * s * np.sqrt(ky * kx), sx, sy)]),
+        ]
+
     def viscosity(self):
         return self.nu
 
@@ -257,6 +289,20 @@ class TaylorGreenVortex(FluidFlowProblem):
         ux, uy = self.velocity(x, y, 0.0)
         s = 2 * self.viscosity()
         return s * ux, s * uy
+
+    def expected_separable(self, q, t, y0=0, ny=None):
+        x, y = self._xy(y0, ny)
+        a, A, b, B = self.a, self.A, self.b, self.B
+        d = self.decay(x, y, t)
+        nu = self.viscosity()
+        K = q.speed_of_sound_squared * self.u_max ** 2 * (-(1 / 4) * self.rho_0 * d ** 2)
+        cx, sx, cy, sy = np.cos(a * x), np.sin(a * x), np.cos(b * y), np.sin(b * y)
+        p = (1.0, [(K * A ** 2, np.cos(2 * a * x), None), (K * B ** 2, None, np.cos(2 * b * y))])
+        return [p, (0.0, [(d * A, cx, sy)]), (0.0, [(d * B, sx, cy)]), p,
+                (0.0, [(-nu * 2 * d * (-a * A), sx, sy)]),
+                (0.0, [(-nu * d * (a * B + b * A), cx, cy)]),
+                (0.0, [(-nu * d * (a * B + b * A), cx, cy)]),
+                (0.0, [(-nu * 2 * d * (-b * B), sx, sy)])]
 
 
 class DecayingShearFlow(FluidFlowProblem):
@@ -326,6 +372,20 @@ class DecayingShearFlow(FluidFlowProblem):
         nu = self.viscosity()
         return (nu * ky ** 2 * A * np.cos(ky * y - ky * B * t) + z, nu * kx ** 2 * B * np.cos(kx * x - kx * A * t) + z)
 
+    def expected_separable(self, q, t, y0=0, ny=None):
+        x, y = self._xy(y0, ny)
+        A, B, kx, ky = self.A, self.B, self.k_x, self.k_y
+        nu = self.viscosity()
+        ex = 1.0 if self.static else np.exp(-1.0 * kx ** 2 * nu * t)
+        ey = 1.0 if self.static else np.exp(-1.0 * ky ** 2 * nu * t)
+        dec = self.decay(x, y, t)
+        p = (1.0, [(B * 0.025 * q.speed_of_sound_squared * self.u_max ** 2 * B * dec ** 2, np.sin(kx * (x - A * t)) ** 2, None)])
+        u_y = -A * ky * np.sin(ky * (y - B * t)) * ey   # d u_x / d y, function of y
+        v_x = -B * kx * np.sin(kx * (x - A * t)) * ex   # d u_y / d x, function of x
+        sxy = (0.0, [(-nu, v_x, None), (-nu, None, u_y)])
+        return [(1.0, []), (0.0, [(A * ey, None, np.cos(ky * y - ky * B * t))]), (0.0, [(B * ex, np.cos(kx * x - kx * A * t), None)]),
+                p, (0.0, []), sxy, sxy, (0.0, [])]
+
     def force_separable(self, t0, nsteps, y0=0, ny=None):
         """Lattice force of steps t0..t0+nsteps-1 as F_x(y, t), F_y(x, t) tables: the force above is
         a sum of a function of (y, t) and one of (x, t) (decaying_shear_flow.jl:131-147)."""
@@ -392,6 +452,12 @@ class PoiseuilleFlow(FluidFlowProblem):
         # force(problem, x::Int, y::Int, t) poiseuille.jl:72-82 -- uniform
         return (self.viscosity() * self.G, 0.0)
 
+    def expected_separable(self, q, t, y0=0, ny=None):
+        x, y = self._xy(y0, ny)
+        L, G, nu = self.domain_size[1], self.G, self.viscosity()
+        sxy = (0.0, [(-nu, None, (L - 2 * y) * (G / 2))])
+        return [(1.0, []), (0.0, [(1.0, None, y * (L - y) * (G / 2))]), (0.0, []), (1.0, []), (0.0, []), sxy, sxy, (0.0, [])]
+
     def force_uniform(self):
         s = self.u_max * self.delta_t()
         F = self.force_idx(1, 1)
@@ -436,6 +502,11 @@ class CouetteFlow(FluidFlowProblem):
 
     def force_idx(self, x_idx, y_idx, t=0.0):
         return (0.0, 0.0)
+
+    def expected_separable(self, q, t, y0=0, ny=None):
+        x, y = self._xy(y0, ny)
+        nu = self.viscosity()
+        return [(1.0, []), (0.0, [(1.0, None, y)]), (0.0, []), (1.0, []), (0.0, []), (-nu, []), (-nu, []), (0.0, [])]
 
     def boundary_conditions(self):
         return [BounceBack(South(), (1, self.NX), (1, self.NY)),

@@ -559,3 +559,28 @@ def test_couette_moving_wall_steady_state(oracle, name):
         assert abs(got[k] - want[k]) <= 1e-9 * abs(want[k]) + 1e-14, (name, k, got[k], want[k])
     assert rel_max(to_oracle_layout(model.f_stream), mo.f_stream) < 1e-12
     model.close()
+
+
+@pytest.mark.parametrize("name", ["D2Q9", "D2Q17", "D2Q37"])
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_device_error_norms_match_host_path(name, dtype):
+    """lbm_reduce_errors (16 sums on the device, separable analytic fields) == the field-download path."""
+    q = getattr(lbm.Quadratures, name)
+    cases = [(lbm.TGV(q, 0.8, 1, 24, 16), lbm.TRT), (lbm.TaylorGreenVortex(1 / 6, 1, 16, 16), lbm.SRT),
+             (lbm.DecayingShearFlow.fields(1.0, 0.01, 1 / 6, 16, 12, (2 * np.pi, 2 * np.pi), True, 1.0, 1.0, 1.0, 1.0), lbm.SRT),
+             (lbm.PoiseuilleFlow.fields(1.0, 0.02, 1 / 6, 6, 12, 1.0, (1.0, 1.0), 1.0), lbm.TRT),
+             (lbm.CouetteFlow.fields(1.0, 0.01, 1 / 6, 4, 10, (1.0, 1.0)), lbm.SRT)]
+    for problem, cm in cases:
+        rows = []
+        for device_norms in (True, False):
+            pm = lbm.TrackHydrodynamicErrors(problem, False, 25, lbm.NoStoppingCriteria(), device_norms=device_norms)
+            m = lbm.LatticeBoltzmannModel(problem, q, collision_model=cm, process_method=pm, dtype=dtype)
+            lbm.simulate(m, range(0, 25))
+            m.close()
+            rows.append(pm.df[-1])
+        a, b = rows
+        for k, v in b.items():
+            if np.isfinite(v) and v != 0:
+                assert abs(a[k] - v) <= 1e-9 * abs(v), (type(problem).__name__, k, a[k], v)
+            else:
+                assert (np.isnan(a[k]) and np.isnan(v)) or a[k] == v or (np.isinf(a[k]) and np.isinf(v)), (k, a[k], v)

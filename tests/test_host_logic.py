@@ -264,3 +264,27 @@ def test_slab_decomposition_world2_gloo(lattice, with_walls):
     for rank, y0, slab, total in results:
         assert np.array_equal(slab, f[:, y0:y0 + slab.shape[1]]), f"rank {rank} slab differs from the single-domain run"
         assert total[1] == ny * nx and np.isclose(total[0], O.density(qo, [f[i] for i in range(qo.Q)]).sum(), rtol=1e-14)
+
+
+def test_separable_expected_fields_reproduce_the_analytic_fields():
+    """problem.expected_separable (input of lbm_reduce_errors) == density/velocity/pressure/deviatoric_tensor."""
+    q = lbm.D2Q9()
+    probs = [lbm.TGV(q, 0.8, 1, 8, 12), lbm.TaylorGreenVortex(1 / 6, 1, 8, 8), lbm.TaylorGreenVortex(1 / 6, 1, 8, 8, static=False),
+             lbm.DecayingShearFlow(1 / 6, 2), lbm.DecayingShearFlow(1 / 6, 2, static=False, k_y=1.0),
+             lbm.PoiseuilleFlow(1 / 6, 2), lbm.CouetteFlow(1 / 6, 2)]
+    for pr in probs:
+        for t in (0.0, 0.37):
+            for y0, ny in ((0, None), (1, 2)):
+                sep = pr.expected_separable(q, t, y0, ny)
+                X, Y = pr.grid(y0, ny)
+                (sxx, sxy), (syx, syy) = pr.deviatoric_tensor(q, X, Y, t)
+                ux, uy = pr.velocity(X, Y, t)
+                ref = [pr.density(q, X, Y, t), ux, uy, pr.pressure(q, X, Y, t), sxx, sxy, syx, syy]
+                for f, (c0, terms) in enumerate(sep):
+                    E = c0 + 0 * X
+                    for a, Xt, Yt in terms:
+                        xv = np.ones(X.shape[0]) if Xt is None else Xt
+                        yv = np.ones(X.shape[1]) if Yt is None else Yt
+                        E = E + a * xv[:, None] * yv[None, :]
+                    assert np.abs(E - ref[f]).max() <= 1e-13 * max(np.abs(ref[f]).max(), 1e-300), (type(pr).__name__, t, f)
+    assert lbm.LidDrivenCavityFlow(1 / 6, 1).expected_separable(q, 0.0) is None
