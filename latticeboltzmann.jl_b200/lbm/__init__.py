@@ -17,7 +17,8 @@ from .initial_conditions import (AnalyticalEquilibrium, AnalyticalEquilibriumAnd
 from .model import (DeviceState, LatticeBoltzmannModel, apply_, apply_boundary_conditions_, collide_,
                     collide_model_, next_model_, simulate, simulate_model, stream_, stream_model_)
 from .parallel import SlabComm, halo_rows_per_direction, slab_rows
-from .problems import (CouetteFlow, DecayingShearFlow, FluidFlowProblem, LidDrivenCavityFlow, PoiseuilleFlow, TGV,
+from .problems import (CouetteFlow, DecayingShearFlow, FluidFlowProblem, LidDrivenCavityFlow,
+                       LinearizedThermalDiffusion, LinearizedTransverseShearWave, PoiseuilleFlow, TGV,
                        TaylorGreenVortex, boundary_conditions, decay_time, delta_t, delta_x, has_external_force,
                        lattice_force, lattice_viscosity, viscosity)
 from .processing_methods import (CompareWithAnalyticalSolution, MeanVelocityStoppingCriteria, NoStoppingCriteria,

@@ -539,3 +539,67 @@ class LidDrivenCavityFlow(FluidFlowProblem):
         return [BounceBack(East(), (1, self.NX), (1, self.NY)), BounceBack(South(), (1, self.NX), (1, self.NY)),
                 BounceBack(West(), (1, self.NX), (1, self.NY)),
                 MovingWall(North(), (1, self.NX), (1, self.NY), [self.u_max, 0])]
+
+
+class _LinearizedMode(FluidFlowProblem):
+    """Common fields of the two linearised hydrodynamic modes (linear_hydrodynamics_modes.jl)."""
+
+    def __init__(self, nu, kappa, scale, NY):
+        self.rho_0, self.theta_0 = 1.0, 1.0
+        self.rho_tilde, self.u_tilde = 0.001, 0.001
+        self.nu, self.kappa = nu, kappa
+        self.domain_size = (2 * np.pi, 2 * np.pi)
+        self.u_max = 0.01 / scale
+        self.NX = self.NY = int(NY)
+
+    def delta_x(self):
+        return self.domain_size[1] / self.NY
+
+    def heat_diffusion(self):
+        return self.kappa * self.delta_x() ** 2 / self.delta_t()  # problems.jl:81-82
+
+
+class LinearizedThermalDiffusion(_LinearizedMode):
+    """LinearizedThermalDiffusion(nu, kappa, scale, NY = 4 scale): rho = rho_0 + rho~ sin(y) exp(-kappa t), u = 0,
+    p = rho_0 theta_0 (linear_hydrodynamics_modes.jl:15-99)."""
+
+    def __init__(self, nu, kappa, scale, NY=None):
+        super().__init__(nu, kappa, scale, 4 * scale if NY is None else NY)
+
+    def density(self, q, x, y, t=0.0):
+        return self.rho_0 + self.rho_tilde * np.sin(y) * np.exp(-self.heat_diffusion() * t) + 0.0 * np.asarray(x, dtype=np.float64)
+
+    def pressure(self, q, x, y, t=0.0):
+        return self.rho_0 * self.theta_0 + 0.0 * (np.asarray(x, dtype=np.float64) + y)
+
+    def velocity(self, x, y, t=0.0):
+        z = 0.0 * (np.asarray(x, dtype=np.float64) + y)
+        return z, z
+
+    def expected_separable(self, q, t, y0=0, ny=None):
+        x, y = self._xy(y0, ny)
+        return [(self.rho_0, [(self.rho_tilde * np.exp(-self.heat_diffusion() * t), None, np.sin(y))]), (0.0, []), (0.0, []),
+                (self.rho_0 * self.theta_0, []), (0.0, []), (0.0, []), (0.0, []), (0.0, [])]
+
+
+class LinearizedTransverseShearWave(_LinearizedMode):
+    """LinearizedTransverseShearWave(nu, kappa, scale, NY = 8 scale): rho = rho_0, u = [u~ sin(y) exp(-nu t), 0],
+    p = theta_0 (linear_hydrodynamics_modes.jl:101-178)."""
+
+    def __init__(self, nu, kappa, scale, NY=None):
+        super().__init__(nu, kappa, scale, 8 * scale if NY is None else NY)
+
+    def density(self, q, x, y, t=0.0):
+        return self.rho_0 + 0.0 * (np.asarray(x, dtype=np.float64) + y)
+
+    def pressure(self, q, x, y, t=0.0):
+        return self.theta_0 + 0.0 * (np.asarray(x, dtype=np.float64) + y)
+
+    def velocity(self, x, y, t=0.0):
+        z = 0.0 * (np.asarray(x, dtype=np.float64) + y)
+        return self.u_tilde * np.sin(y) * np.exp(-self.viscosity() * t) + z, z
+
+    def expected_separable(self, q, t, y0=0, ny=None):
+        x, y = self._xy(y0, ny)
+        return [(self.rho_0, []), (0.0, [(self.u_tilde * np.exp(-self.viscosity() * t), None, np.sin(y))]), (0.0, []),
+                (self.theta_0, []), (0.0, []), (0.0, []), (0.0, []), (0.0, [])]

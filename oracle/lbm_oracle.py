@@ -842,6 +842,49 @@ class LidDrivenCavityFlow(Problem):
                 MovingWall("N", (1, self.NX), (1, self.NY), [self.u_max, 0])]
 
 
+class LinearizedThermalDiffusion(Problem):
+    """linear_hydrodynamics_modes.jl:15-99."""
+
+    def __init__(self, nu, kappa, scale, NY=None):
+        NY = 4 * scale if NY is None else NY
+        self.rho_0, self.theta_0, self.rho_t, self.u_t = 1.0, 1.0, 0.001, 0.001
+        self.nu, self.kappa = nu, kappa
+        self.domain_size = (2 * np.pi, 2 * np.pi)
+        self.u_max = 0.01 / scale
+        self.NX = self.NY = NY
+
+    def delta_x(self):
+        return self.domain_size[1] / self.NY
+
+    def heat_diffusion(self):
+        return self.kappa * self.delta_x() ** 2 / self.delta_t()
+
+    def density(self, q, x, y, t=0.0):
+        return self.rho_0 + self.rho_t * np.sin(y) * np.exp(-self.heat_diffusion() * t) + 0.0 * x
+
+    def pressure(self, q, x, y, t=0.0):
+        return self.rho_0 * self.theta_0 + 0.0 * x
+
+    def velocity(self, x, y, t=0.0):
+        return 0.0 * x, 0.0 * x
+
+
+class LinearizedTransverseShearWave(LinearizedThermalDiffusion):
+    """linear_hydrodynamics_modes.jl:101-178."""
+
+    def __init__(self, nu, kappa, scale, NY=None):
+        super().__init__(nu, kappa, scale, 8 * scale if NY is None else NY)
+
+    def density(self, q, x, y, t=0.0):
+        return self.rho_0 + 0.0 * x
+
+    def pressure(self, q, x, y, t=0.0):
+        return self.theta_0 + 0.0 * x
+
+    def velocity(self, x, y, t=0.0):
+        return self.u_t * np.sin(y) * np.exp(-self.viscosity() * t) + 0.0 * x, 0.0 * x
+
+
 # --------------------------------------------------------------------------
 # Collision-model factories (srt.jl:7-16, trt.jl:8-21,35-40, mrt.jl:36-47)
 # --------------------------------------------------------------------------

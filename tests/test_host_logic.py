@@ -21,6 +21,10 @@ PAIRS = [
     ("PoiseuilleFlow", lambda q: lbm.PoiseuilleFlow(1 / 6, 2), lambda q: O.PoiseuilleFlow(1 / 6, 2)),
     ("CouetteFlow", lambda q: lbm.CouetteFlow(1 / 6, 2), lambda q: O.CouetteFlow(1 / 6, 2)),
     ("LidDrivenCavityFlow", lambda q: lbm.LidDrivenCavityFlow(1 / 6, 1), lambda q: O.LidDrivenCavityFlow(1 / 6, 1)),
+    ("LinearizedThermalDiffusion", lambda q: lbm.LinearizedThermalDiffusion(1 / 6, 1 / 6, 2),
+     lambda q: O.LinearizedThermalDiffusion(1 / 6, 1 / 6, 2)),
+    ("LinearizedTransverseShearWave", lambda q: lbm.LinearizedTransverseShearWave(1 / 6, 1 / 6, 2),
+     lambda q: O.LinearizedTransverseShearWave(1 / 6, 1 / 6, 2)),
 ]
 
 
@@ -271,7 +275,8 @@ def test_separable_expected_fields_reproduce_the_analytic_fields():
     q = lbm.D2Q9()
     probs = [lbm.TGV(q, 0.8, 1, 8, 12), lbm.TaylorGreenVortex(1 / 6, 1, 8, 8), lbm.TaylorGreenVortex(1 / 6, 1, 8, 8, static=False),
              lbm.DecayingShearFlow(1 / 6, 2), lbm.DecayingShearFlow(1 / 6, 2, static=False, k_y=1.0),
-             lbm.PoiseuilleFlow(1 / 6, 2), lbm.CouetteFlow(1 / 6, 2)]
+             lbm.PoiseuilleFlow(1 / 6, 2), lbm.CouetteFlow(1 / 6, 2), lbm.LinearizedThermalDiffusion(1 / 6, 1 / 6, 2),
+             lbm.LinearizedTransverseShearWave(1 / 6, 1 / 6, 2)]
     for pr in probs:
         for t in (0.0, 0.37):
             for y0, ny in ((0, None), (1, 2)):
