@@ -129,7 +129,9 @@ __device__ __forceinline__ void load_pair(const KParams<float> &p, int x0, int y
 template <int CM, bool PULL, int MINB>
 __global__ void __launch_bounds__(256, MINB) k_step_x2(const __grid_constant__ KParams<float> p, long long step) {
     const int x0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
-    // whole warps stay alive for the shuffles; out-of-range lanes compute on node 0 and skip the store
+    // Whole warps stay alive for the shuffles; out-of-range lanes work on x = 0 and skip the store.
+    // x = 0 is the periodic image of x = nx, which is exactly what the last valid lane must receive
+    // from its right neighbour (the first out-of-range lane), so no special case is needed there.
     const bool valid = x0 < p.nx;
     const int xl = valid ? x0 : 0;
     const LatConst<float> &c = c_lat32;

@@ -516,7 +516,12 @@ def test_shear_wave_convergence_is_second_order(oracle, name):
     for a, b in zip(errs, errs_o):
         assert abs(a - b) <= 1e-9 * abs(b), (errs, errs_o)
     slope = np.polyfit(np.log([8.0 * s for s in scales]), np.log(errs), 1)[0]
-    assert slope <= -1.8, (name, errs, slope)
+    if name in ("D2Q4", "D2Q5"):
+        # first-order lattices: the reference algorithm itself does not converge on this problem
+        # (oracle: error_u stays at 4.4 / 1.55); what must hold is agreement with the oracle (above)
+        assert abs(slope) < 0.1
+    else:
+        assert slope <= -1.8, (name, errs, slope)
 
 
 @pytest.mark.parametrize("model", ["SRT", "TRT", "MRT"])
@@ -584,3 +589,40 @@ def test_device_error_norms_match_host_path(name, dtype):
                 assert abs(a[k] - v) <= 1e-9 * abs(v), (type(problem).__name__, k, a[k], v)
             else:
                 assert (np.isnan(a[k]) and np.isnan(v)) or a[k] == v or (np.isinf(a[k]) and np.isinf(v)), (k, a[k], v)
+
+
+def test_bench_contract_small():
+    """bench.py prints exactly one JSON line on stdout with the contract's keys (small grid, seconds)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--nx", "256", "--ny", "256", "--steps", "2",
+                          "--warmup", "3", "--inner", "20", "--cpu-n", "128", "--cpu-steps", "10"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["unit"] == "MLUPS" and d["value"] > 0 and d["gpu_launches"] == 2 * 20 and d["n_gpus"] == 1
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(d["roofline"])
+    assert d["roofline"]["bound"] == "hbm" and 0 < d["roofline"]["frac"] < 1.5
+    assert d["e2e"]["h2d_bytes_per_step"] == 256 * 256 * 9 * 8 == d["e2e"]["d2h_bytes_per_step"] and d["e2e"]["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert "workload" in d["config"]
+
+
+def test_timer_and_options():
+    with _abi.Context(64, 64, "D2Q9", _abi.SRT, [0.9]) as c:
+        c.upload_f(np.asfortranarray(np.ones((64, 64, 9)) * lbm.D2Q9().weights))
+        c.timer_start()
+        c.step(0, 10)
+        assert c.timer_stop() > 0 and c.last_step_ms() > 0
+        assert c.kernel_launches >= 10
+        with pytest.raises(lbm.LbmError):
+            c.set_option("no_such_option", 1)
+        c.set_option("overlap", 0)
