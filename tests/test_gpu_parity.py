@@ -586,7 +586,8 @@ def test_device_error_norms_match_host_path(name, dtype):
         a, b = rows
         for k, v in b.items():
             if np.isfinite(v) and v != 0:
-                assert abs(a[k] - v) <= 1e-9 * abs(v), (type(problem).__name__, k, a[k], v)
+                # (sums that vanish analytically, e.g. the TGV momentum, are pure round-off ~1e-18)
+                assert abs(a[k] - v) <= 1e-9 * abs(v) + 1e-13, (type(problem).__name__, k, a[k], v)
             else:
                 assert (np.isnan(a[k]) and np.isnan(v)) or a[k] == v or (np.isinf(a[k]) and np.isinf(v)), (k, a[k], v)
 
