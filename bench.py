@@ -5,8 +5,9 @@
 
 Workload (N = 1): BASELINE.json configs[1] -- D2Q9 TRT Taylor-Green vortex decay, 4096 x 4096
 periodic, Float64 (TGV(D2Q9(), 0.8, 256); CollisionModel(TRT, ...): tau_s = 0.8, Lambda = 1/4).
-N > 1: y-slab weak scaling, one 4096 x 4096 slab per GPU (global NY = 4096 N), halos exchanged
-inside liblbm_b200.so with NCCL send/recv on a side stream.
+N > 1: y-slab weak scaling, one 4096 x 4096 slab per GPU (global NY = 4096 N); the launch that computes a
+slab's boundary rows stores them straight into the neighbours' ghost rows over NVLink (peer memory, device-side
+flags); `--p2p 0` selects the NCCL send/recv path on a side stream instead.
 
 One bench "step" = one device batch of `--inner` (default 100) lattice time steps: 100 is the
 reference's host-visible cadence (`next!` checks its stop criterion every 100 steps,
@@ -58,6 +59,7 @@ def parse():
     ap.add_argument("--variant", type=int, default=int(os.environ.get("LBM_BENCH_VARIANT", "0")))
     ap.add_argument("--config", default="C2", choices=["C2", "C3", "C4", "C5s", "C5w"],
                     help="BASELINE.json config preset (C2 = default bench workload; see build_case)")
+    ap.add_argument("--p2p", type=int, default=1, help="N > 1: 1 = peer-memory halo stores (default), 0 = NCCL send/recv")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-n", type=int, default=1024)
@@ -244,6 +246,8 @@ def run_b200(a):
     q, problem, cm, nx, ny, scaling = case["q"], case["problem"], case["cm"], case["nx"], case["ny"], case["scaling"]
     ctx = lbm.model.make_context(q, cm, problem.boundary_conditions(), nx, ny, a.dtype, a.arith, comm, local)
     ctx.set_option("variant", a.variant)
+    ctx.set_option("p2p", a.p2p)
+    halo_path = {0: "none (single GPU)", 1: "NCCL send/recv on a side stream", 2: "peer-memory stores from the boundary-row launch"}[ctx.halo_path]
     nyl = ctx.ny_local
     state = lbm.DeviceState(ctx, q, cm, comm)
     state.prepare_force(0, 1, problem.delta_t())
@@ -342,7 +346,7 @@ def run_b200(a):
             "dtype": a.dtype, "data": "synthetic",
             "config": {"workload": case["workload"], "preset": a.config,
                        "grid_per_gpu": [nx, nyl], "grid_global": [nx, ny], "lattice_steps_per_bench_step": inner,
-                       "arith": a.arith, "variant": a.variant, "parallelism": f"y-slabs x{world}",
+                       "arith": a.arith, "variant": a.variant, "parallelism": f"y-slabs x{world}", "halo_exchange": halo_path,
                        "l2": "working set (2 x %.2f GB per GPU) >> 126 MB L2; no flush needed" % (nx * nyl * q.Q * BYTES[a.dtype] / 1e9),
                        "wall_ms_per_step": region_ms / a.steps},
             "clocks": clocks,

@@ -174,7 +174,7 @@ int lbm_reduce(lbm_ctx *ctx, int32_t kind, double *out, int32_t n);
 
 /* TrackHydrodynamicErrors.next! (processing_methods/track_hydrodynamic_errors.jl:114-203) without moving fields
  * to the host.  The problem's analytic fields density/velocity/pressure/deviatoric_tensor(q, problem, x, y, t)
- * (src/problems/*.jl) are passed in separable form -- every shipped problem's fields are sums of at most two
+ * (the files of src/problems) are passed in separable form -- every shipped problem's fields are sums of at most two
  * products of a function of x and a function of y:
  *     E(x, y) = c0 + a[0] x[0][x] y[0][y] + a[1] x[1][x] y[1][y]      (x[k] / y[k] == NULL: all ones)
  * expected[0..7] = rho, u_x, u_y, p, sigma_xx, sigma_xy, sigma_yx, sigma_yy (dimensionless units); x tables have nx
@@ -192,6 +192,11 @@ int lbm_reduce_errors(lbm_ctx *ctx, double tau_visc, double u_max, const lbm_sep
 
 /* Introspection used by bench.py / tests. */
 int64_t lbm_kernel_launches(const lbm_ctx *ctx); /* kernels launched by this context so far */
+/* How halos travel between y-slabs: 0 = single GPU (ghost cells written by the kernels themselves), 1 = NCCL
+ * send/recv on a side stream, 2 = peer memory (the boundary-row launch stores into the neighbours' ghost rows over
+ * NVLink and hand-shakes through device-side flags; chosen at lbm_create when every rank could map its
+ * neighbours' buffers, lbm_set_option("p2p", 0) or LBM_P2P=0 select 1). */
+int lbm_halo_path(const lbm_ctx *ctx);
 int lbm_last_step_ms(lbm_ctx *ctx, float *ms);    /* CUDA-event time of the last lbm_step batch */
 /* CUDA events on the library's own stream (torch.cuda.Event cannot see it): start, ...work..., stop
  * (synchronises and returns the elapsed device time). */

@@ -18,6 +18,18 @@ struct BCd {  // device view of one boundary condition (global, 1-based inclusiv
     double ax, ay;  // MovingWall: equilibrium_coefficient(Val{1}) = rho_w * u_w (moving_wall.jl:20)
 };
 
+// slots of the per-context flag block used by the peer-memory halo protocol (unsigned long long each)
+enum {
+    P2P_EPOCH_FROM_DOWN = 0,  // last epoch published by the down neighbour
+    P2P_EPOCH_FROM_UP = 1,    // ... by the up neighbour
+    P2P_TIMEOUT = 2,          // != 0: a wait gave up (protocol error); reported as LBM_ERR_STATE
+    P2P_CTA_COUNT = 3,        // CTAs of the running boundary launch that have finished
+    P2P_BATCH_FROM_DOWN = 4,  // lbm_step batch tokens
+    P2P_BATCH_FROM_UP = 5,
+    P2P_MAGIC = 7,            // written at create time; read through the mapping by the neighbours as a self-check
+    P2P_NFLAGS = 8
+};
+
 template <typename T>
 struct KParams {
     const T *src;  // pulled / read buffer
@@ -51,6 +63,15 @@ struct KParams {
     const T *sep_fx;  // [nsteps][nyl]
     const T *sep_fy;  // [nsteps][nx]
     long long sep_t0;
+    // peer-memory halo exchange (world > 1 with the neighbours' buffers mapped, see kernels_inst.cu): only read by
+    // the P2P instances of the fused kernel
+    T *peer_up, *peer_dn;               // (plane 0, row 0, x 0) of the neighbours' buffer with the same role as dst
+    long long plane_up, plane_dn;       // their plane strides (slabs may differ by one row; the pitch is common)
+    int nyl_dn;                         // rows of the down neighbour (its top ghost rows start there)
+    unsigned long long *flags;          // local flag block, slots P2P_*
+    unsigned long long *flag_at_up;     // up neighbour's flags[P2P_EPOCH_FROM_DOWN]  (I am its `down`)
+    unsigned long long *flag_at_dn;     // down neighbour's flags[P2P_EPOCH_FROM_UP]  (I am its `up`)
+    unsigned long long epoch;           // sequence number of the state this launch produces
     // boundary conditions
     int nbc;
     int bc_sides;  // bit d set: some boundary condition faces direction d (lbm_direction) -> only those edges take the BC path
@@ -90,6 +111,11 @@ struct Ops {
     // collide (+ optional fused pull of the previous step's stream + BCs)
     void (*step64)(int cm, bool pull, const KParams<double> &p, long long step, int variant, cudaStream_t s);
     void (*step32)(int cm, bool pull, const KParams<float> &p, long long step, int variant, cudaStream_t s);
+    // fused pull + collide of boundary rows that also pushes them into the neighbours' ghost rows (peer memory)
+    void (*step64_p2p)(int cm, const KParams<double> &p, long long step, int variant, cudaStream_t s);
+    void (*step32_p2p)(int cm, const KParams<float> &p, long long step, int variant, cudaStream_t s);
+    void (*p2p_barrier)(unsigned long long *flags, unsigned long long *at_up, unsigned long long *at_dn, unsigned long long token, cudaStream_t s);
+    void (*p2p_wait_epoch)(unsigned long long *flags, unsigned long long need, cudaStream_t s);
     // periodic pull (+ BCs when p.nbc > 0) without collision
     void (*stream64)(const KParams<double> &p, cudaStream_t s);
     void (*stream32)(const KParams<float> &p, cudaStream_t s);

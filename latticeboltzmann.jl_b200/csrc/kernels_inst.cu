@@ -458,16 +458,125 @@ __device__ __forceinline__ bool load_force(const KParams<T> &p, int x, int y, lo
 }
 
 // ------------------------------------------------------------------------------------------
+// peer-memory halo exchange (device side; y-slabs, world > 1, after the peers' buffers were mapped)
+// ------------------------------------------------------------------------------------------
+// The launch that produces a slab's 2H boundary rows writes them straight into the neighbours' ghost rows
+// over NVLink and hand-shakes through flags in peer memory: no NCCL call and no copy kernel in the step
+// loop.  Protocol (KParams::flags): the launch producing state `epoch`
+//   1. waits until both neighbours have published epoch - 1: their boundary rows of that state are then in
+//      my ghost rows, and their boundary launch no longer reads the ghost rows (of the other buffer, which
+//      is the one with the role of my dst) that I am about to overwrite;
+//   2. computes its rows, stores them locally and into the neighbours' ghost rows;
+//   3. the last CTA to finish publishes `epoch` to both neighbours (release at system scope).
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Spin (one thread) until flags[a] >= need and flags[b] >= need.  Bounded: a protocol error sets
+// flags[P2P_TIMEOUT] (reported by the host as LBM_ERR_STATE) instead of hanging the GPU.
+__device__ __noinline__ void p2p_spin(unsigned long long *flags, int a, int b, unsigned long long need, unsigned long long limit_ns) {
+    if (ld_acquire_sys(flags + a) >= need && ld_acquire_sys(flags + b) >= need) return;
+    const unsigned long long t0 = globaltimer_ns();
+    while (ld_acquire_sys(flags + a) < need || ld_acquire_sys(flags + b) < need) {
+        if (globaltimer_ns() - t0 > limit_ns) { atomicMax(flags + P2P_TIMEOUT, need ? need : 1ULL); break; }
+        __nanosleep(100);
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void p2p_wait(const KParams<T> &p) {
+    if (threadIdx.x == 0 && threadIdx.y == 0) p2p_spin(p.flags, P2P_EPOCH_FROM_DOWN, P2P_EPOCH_FROM_UP, p.epoch - 1, 10000000000ULL);
+    __syncthreads();
+}
+
+// After a boundary node has been stored locally: copy the populations the neighbour will pull (c_y > 0 at
+// least as large as the distance to my top edge go up, c_y < 0 go down) and their x images into its ghost rows.
+template <typename T>
+__device__ __noinline__ void p2p_store(const KParams<T> &p, int x, int y) {
+    const T *d = p.dst + (long long)y * p.pitch + x;
+    const int kx_lo = -((x + H) / p.nx), kx_hi = (p.nx + H - 1 - x) / p.nx;
+    if (y >= p.nyl - H && p.peer_up) {  // my top rows are the up neighbour's bottom ghost rows -H .. -1
+        const int dist = p.nyl - y;
+        T *g = p.peer_up + (long long)(y - p.nyl) * p.pitch + x;
+        static_for<0, Q>([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            if constexpr (L::cy(i) > 0) {
+                if (L::cy(i) >= dist) {
+                    const T v = d[i * p.plane];
+                    for (int kx = kx_lo; kx <= kx_hi; ++kx) g[i * p.plane_up + kx * p.nx] = v;
+                }
+            }
+        });
+    }
+    if (y < H && p.peer_dn) {  // my bottom rows are the down neighbour's top ghost rows nyl_dn .. nyl_dn + H - 1
+        const int dist = y + 1;
+        T *g = p.peer_dn + (long long)(p.nyl_dn + y) * p.pitch + x;
+        static_for<0, Q>([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            if constexpr (L::cy(i) < 0) {
+                if (-L::cy(i) >= dist) {
+                    const T v = d[i * p.plane];
+                    for (int kx = kx_lo; kx <= kx_hi; ++kx) g[i * p.plane_dn + kx * p.nx] = v;
+                }
+            }
+        });
+    }
+}
+
+// End of a producing launch: every thread makes its (peer) stores visible system-wide, the last CTA to
+// finish publishes the epoch to both neighbours.
+template <typename T>
+__device__ __forceinline__ void p2p_signal(const KParams<T> &p) {
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        const unsigned long long total = (unsigned long long)gridDim.x * gridDim.y;
+        if (atomicAdd(p.flags + P2P_CTA_COUNT, 1ULL) == total - 1) {
+            p.flags[P2P_CTA_COUNT] = 0;
+            __threadfence_system();
+            st_release_sys(p.flag_at_up, p.epoch);
+            st_release_sys(p.flag_at_dn, p.epoch);
+        }
+    }
+}
+
+// Stream-ordered host-side hooks (one thread).
+// k_p2p_barrier: start of an lbm_step batch -- tell both neighbours that everything this rank enqueued before
+// the batch has finished, and wait for the same from them (after it, nobody reads or writes ghost rows
+// outside the protocol above).  k_p2p_wait_epoch: end of a batch -- the last state's halos have landed.
+__global__ void k_p2p_barrier(unsigned long long *flags, unsigned long long *at_up, unsigned long long *at_dn, unsigned long long token) {
+    __threadfence_system();
+    st_release_sys(at_up, token);
+    st_release_sys(at_dn, token);
+    p2p_spin(flags, P2P_BATCH_FROM_DOWN, P2P_BATCH_FROM_UP, token, 120000000000ULL);
+}
+__global__ void k_p2p_wait_epoch(unsigned long long *flags, unsigned long long need) {
+    p2p_spin(flags, P2P_EPOCH_FROM_DOWN, P2P_EPOCH_FROM_UP, need, 10000000000ULL);
+}
+
+// ------------------------------------------------------------------------------------------
 // K1/K2: collide, optionally fused with the pull (stream + BCs) of the previous step
 // ------------------------------------------------------------------------------------------
 // MINB: minimum resident CTAs per SM asked of the register allocator; NPT: consecutive rows handled
 // by one thread (all NPT*Q loads are issued before the first use -> more bytes in flight per thread,
 // which is what the 4-byte populations need to cover the HBM latency).
-template <int CM, typename T, bool PULL, int MINB = 1, int NPT = 1>
+// P2P: the launch takes part in the peer-memory halo protocol above (whole CTAs stay alive for it).
+template <int CM, typename T, bool PULL, int MINB = 1, int NPT = 1, bool P2P = false>
 __global__ void __launch_bounds__(256, MINB) k_step(const __grid_constant__ KParams<T> p, long long step) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= p.nx) return;
-    for (int r0 = (blockIdx.y * blockDim.y + threadIdx.y) * NPT; r0 < p.nrows; r0 += gridDim.y * blockDim.y * NPT) {
+    if constexpr (P2P) p2p_wait(p);
+    else if (x >= p.nx) return;
+    for (int r0 = (!P2P || x < p.nx) ? (blockIdx.y * blockDim.y + threadIdx.y) * NPT : p.nrows; r0 < p.nrows; r0 += gridDim.y * blockDim.y * NPT) {
         T f[NPT][Q];
 #pragma unroll
         for (int j = 0; j < NPT; ++j)
@@ -482,8 +591,12 @@ __global__ void __launch_bounds__(256, MINB) k_step(const __grid_constant__ KPar
                 collide_node<CM, T>(p, f[j], forced, Fx, Fy,
                                     [&](auto I, T v) { p.dstp[decltype(I)::value][n] = v; });
                 store_images(p, x, y);
+                if constexpr (P2P) {
+                    if (y < H || y >= p.nyl - H) p2p_store(p, x, y);
+                }
             }
     }
+    if constexpr (P2P) p2p_signal(p);
 }
 
 // K3: stream (+BC) only:  dst interior = pull(src)
@@ -831,24 +944,29 @@ constexpr StepCfg step_cfg() {
     return {3, 1, 128};
 }
 
-template <int CM, typename T, bool PULL, int MINB, int NPT>
+template <int CM, typename T, bool PULL, int MINB, int NPT, bool P2P = false>
 static void launch_step_cfg(const KParams<T> &p, long long step, int threads, cudaStream_t s) {
     dim3 block; pick_block(p.nx, block);
     if (threads == 128 && block.x >= 128) block = dim3(128, 1, 1);
     dim3 grid = grid_for(p, block, (p.nrows + NPT - 1) / NPT, p.nx);
-    k_step<CM, T, PULL, MINB, NPT><<<grid, block, 0, s>>>(p, step);
+    k_step<CM, T, PULL, MINB, NPT, P2P><<<grid, block, 0, s>>>(p, step);
 }
 
 constexpr int X2_MINB = (Q <= 13) ? 4 : ((Q <= 17) ? 3 : 2);
 
-template <typename T>
-static void launch_step(int cm, bool pull, const KParams<T> &p, long long step, int variant, cudaStream_t s) {
+// P2P = true: the fused (pull) launch that also pushes its boundary rows into the neighbours' ghost rows
+// (same kernel choice and arithmetic as the plain launch, so results do not depend on the exchange path).
+template <typename T, bool P2P>
+static void launch_step_impl(int cm, bool pull, const KParams<T> &p, long long step, int variant, cudaStream_t s) {
     if (p.nrows <= 0) return;
     if constexpr (LBM_FAST && std::is_same<T, float>::value) {
         // Float32 fast mode: packed two-nodes-per-thread kernel (variant 99 forces the scalar one)
         // (measured faster for Q <= 13; the wide lattices run out of registers with 64-bit pairs -- variant 98 forces it)
         if (((Q <= 13 && variant != 99) || variant == 98) && cm != LBM_MRT && p.nx % 2 == 0 && p.nx >= 2) {
-            if (cm == LBM_SRT) {
+            if constexpr (P2P) {
+                if (cm == LBM_SRT) launch_step_x2<LBM_SRT, true, X2_MINB, true>(p, step, s);
+                else launch_step_x2<LBM_TRT, true, X2_MINB, true>(p, step, s);
+            } else if (cm == LBM_SRT) {
                 if (pull) launch_step_x2<LBM_SRT, true, X2_MINB>(p, step, s);
                 else launch_step_x2<LBM_SRT, false, X2_MINB>(p, step, s);
             } else {
@@ -857,6 +975,20 @@ static void launch_step(int cm, bool pull, const KParams<T> &p, long long step, 
             }
             return;
         }
+    }
+    if constexpr (P2P) {
+#define LBM_LAUNCH_P2P(CM)                                                                                        \
+    {                                                                                                             \
+        constexpr StepCfg c = step_cfg<CM, T>();                                                                  \
+        launch_step_cfg<CM, T, true, c.minb, c.npt, true>(p, step, c.threads, s);                                 \
+    }
+        switch (cm) {
+        case LBM_SRT: LBM_LAUNCH_P2P(LBM_SRT) break;
+        case LBM_TRT: LBM_LAUNCH_P2P(LBM_TRT) break;
+        default: LBM_LAUNCH_P2P(LBM_MRT) break;
+        }
+#undef LBM_LAUNCH_P2P
+        return;
     }
 #ifdef LBM_TUNE
     // variant = MINB + 10 * log2(NPT) + 100 * (128-thread CTAs); 0 = production configuration
@@ -880,6 +1012,22 @@ static void launch_step(int cm, bool pull, const KParams<T> &p, long long step, 
     default: LBM_LAUNCH(LBM_MRT) break;
     }
 #undef LBM_LAUNCH
+}
+
+template <typename T>
+static void launch_step(int cm, bool pull, const KParams<T> &p, long long step, int variant, cudaStream_t s) {
+    launch_step_impl<T, false>(cm, pull, p, step, variant, s);
+}
+template <typename T>
+static void launch_step_p2p(int cm, const KParams<T> &p, long long step, int variant, cudaStream_t s) {
+    launch_step_impl<T, true>(cm, true, p, step, variant, s);
+}
+static void launch_p2p_barrier(unsigned long long *flags, unsigned long long *at_up, unsigned long long *at_dn,
+                               unsigned long long token, cudaStream_t s) {
+    k_p2p_barrier<<<1, 1, 0, s>>>(flags, at_up, at_dn, token);
+}
+static void launch_p2p_wait_epoch(unsigned long long *flags, unsigned long long need, cudaStream_t s) {
+    k_p2p_wait_epoch<<<1, 1, 0, s>>>(flags, need);
 }
 
 template <typename T>
@@ -951,6 +1099,8 @@ static void launch_init_eq(const KParams<T> &p, const double *rho, const double 
 static const Ops ops = {
     LBM_LATTICE, LBM_FAST,
     &launch_step<double>, &launch_step<float>,
+    &launch_step_p2p<double>, &launch_step_p2p<float>,
+    &launch_p2p_barrier, &launch_p2p_wait_epoch,
     &launch_stream<double>, &launch_stream<float>,
     &launch_bcs<double>, &launch_bcs<float>,
     &launch_ghosts<double>, &launch_ghosts<float>,

@@ -2,6 +2,7 @@
 // Kernels live in kernels_inst.cu (one instance per <lattice, arithmetic mode>).
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <unistd.h>
 #include <nccl.h>  // types only; the library is dlopen'ed when world > 1
 
 #include <cmath>
@@ -64,6 +65,7 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -85,7 +87,7 @@ static int load_nccl() {
     if (!g_nccl.field) return fail(LBM_ERR_NCCL, "missing NCCL symbol %s", name);
     SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
     SYM(Send, "ncclSend") SYM(Recv, "ncclRecv") SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd")
-    SYM(GetErrorString, "ncclGetErrorString")
+    SYM(GetErrorString, "ncclGetErrorString") SYM(AllReduce, "ncclAllReduce")
 #undef SYM
     g_nccl.handle = h;
     return 0;
@@ -101,6 +103,23 @@ static int load_nccl() {
 // context
 // ----------------------------------------------------------------------------------------------
 enum { ST_STREAM = 0, ST_COLLIDED = 1 };
+
+// What a rank tells its two neighbours about its exported allocation, and the neighbour's view of it.
+struct PeerInfo {
+    cudaIpcMemHandle_t handle;  // of the cudaMalloc allocation that contains the arena
+    unsigned long long offset;  // arena - base of that allocation
+    unsigned long long raw;     // arena address in the owner's process (peers living in the same process)
+    unsigned long long buf_bytes;
+    long long plane;
+    int nyl, pid, device, rank;
+};
+struct PeerMap {
+    PeerInfo info;
+    void *ipc_base = nullptr;  // from cudaIpcOpenMemHandle (nullptr: same process or shared with the other neighbour)
+    char *arena = nullptr;     // neighbour's arena in this process' address space
+};
+static const size_t ARENA_HDR = 4096;
+static const unsigned long long P2P_MAGIC_VALUE = 0x4c424d5032500000ULL;  // "LBMP2P"
 
 struct lbm_ctx {
     lbm_desc desc;
@@ -131,6 +150,14 @@ struct lbm_ctx {
     // multi-GPU
     ncclComm_t comm = nullptr;
     int up = 0, down = 0;
+    // peer-memory halo exchange (world > 1): one exported allocation [flag block | buf 0 | buf 1] per rank
+    void *arena = nullptr;
+    size_t buf_bytes = 0;
+    PeerMap peer_up, peer_dn;
+    bool p2p_on = false;       // neighbours' arenas are mapped and every rank agreed to use them
+    int opt_p2p = 1;           // lbm_set_option("p2p", 0) falls back to NCCL send/recv (same on all ranks)
+    unsigned long long epoch = 0, batch = 0;
+    bool p2p_in_batch = false; // a P2P launch ran in the current lbm_step batch
     long long launches = 0;
     bool timed = false;
     int opt_variant = 0;
@@ -260,6 +287,141 @@ static int post_exchange(lbm_ctx *c, int b) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// peer-memory halo exchange: mapping the neighbours' buffers (cudaIpc, or plain peer access inside one process)
+// ----------------------------------------------------------------------------------------------
+static unsigned long long *my_flags(const lbm_ctx *c) { return reinterpret_cast<unsigned long long *>(c->arena); }
+static unsigned long long *peer_flags(const PeerMap &m) { return reinterpret_cast<unsigned long long *>(m.arena); }
+
+static void p2p_unmap(lbm_ctx *c) {
+    for (PeerMap *m : {&c->peer_up, &c->peer_dn}) {
+        if (m->ipc_base) cudaIpcCloseMemHandle(m->ipc_base);
+        m->ipc_base = nullptr;
+        m->arena = nullptr;
+    }
+    c->p2p_on = false;
+}
+
+static bool p2p_map_one(lbm_ctx *c, PeerMap &m) {
+    if (m.info.pid == (int)getpid()) {
+        if (m.info.device != c->desc.device) {
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, c->desc.device, m.info.device) != cudaSuccess || !can) return false;
+            cudaError_t e = cudaDeviceEnablePeerAccess(m.info.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return false; }
+            cudaGetLastError();
+        }
+        m.arena = reinterpret_cast<char *>(m.info.raw);
+    } else {
+        void *base = nullptr;
+        if (cudaIpcOpenMemHandle(&base, m.info.handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return false; }
+        m.ipc_base = base;
+        m.arena = reinterpret_cast<char *>(base) + m.info.offset;
+    }
+    // self-check through the mapping: the owner wrote MAGIC ^ rank into its flag block
+    unsigned long long v = 0;
+    if (cudaMemcpy(&v, m.arena + P2P_MAGIC * sizeof(unsigned long long), sizeof(v), cudaMemcpyDefault) != cudaSuccess) { cudaGetLastError(); return false; }
+    return v == (P2P_MAGIC_VALUE ^ (unsigned long long)m.info.rank);
+}
+
+// Collective over all ranks of the communicator (called from lbm_create when world > 1).
+static int p2p_connect(lbm_ctx *c) {
+    PeerInfo mine;
+    memset(&mine, 0, sizeof(mine));
+    int local_ok = 1;
+    if (const char *e = getenv("LBM_P2P")) if (atoi(e) == 0) local_ok = 0;
+    // base of the cudaMalloc allocation the arena lives in (small arenas may be sub-allocated)
+    unsigned long long base = (unsigned long long)c->arena;
+    {
+        typedef int (*GetRange)(unsigned long long *, size_t *, unsigned long long);
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr) == cudaSuccess && fn && qr == cudaDriverEntryPointSuccess) {
+            unsigned long long b = 0; size_t sz = 0;
+            if (((GetRange)fn)(&b, &sz, (unsigned long long)c->arena) == 0 && b) base = b;
+        }
+        cudaGetLastError();
+    }
+    if (cudaIpcGetMemHandle(&mine.handle, (void *)base) != cudaSuccess) { cudaGetLastError(); local_ok = 0; }
+    mine.offset = (unsigned long long)c->arena - base;
+    mine.raw = (unsigned long long)c->arena;
+    mine.buf_bytes = c->buf_bytes;
+    mine.plane = c->plane;
+    mine.nyl = c->nyl; mine.pid = (int)getpid(); mine.device = c->desc.device; mine.rank = c->desc.rank;
+    const unsigned long long magic = P2P_MAGIC_VALUE ^ (unsigned long long)c->desc.rank;
+    CU(cudaMemcpy(my_flags(c) + P2P_MAGIC, &magic, sizeof(magic), cudaMemcpyHostToDevice));
+
+    // ship the descriptors to both neighbours with the communicator we already have
+    char *dev = nullptr;
+    CU(cudaMalloc(&dev, 3 * sizeof(PeerInfo) + 16));
+    cudaError_t e = cudaMemcpy(dev, &mine, sizeof(mine), cudaMemcpyHostToDevice);
+    ncclResult_t r = ncclSuccess;
+    if (e == cudaSuccess) {
+        g_nccl.GroupStart();
+        ncclResult_t r1 = g_nccl.Send(dev, sizeof(PeerInfo), ncclChar, c->up, c->comm, c->stream);
+        ncclResult_t r2 = g_nccl.Send(dev, sizeof(PeerInfo), ncclChar, c->down, c->comm, c->stream);
+        ncclResult_t r3 = g_nccl.Recv(dev + sizeof(PeerInfo), sizeof(PeerInfo), ncclChar, c->down, c->comm, c->stream);
+        ncclResult_t r4 = g_nccl.Recv(dev + 2 * sizeof(PeerInfo), sizeof(PeerInfo), ncclChar, c->up, c->comm, c->stream);
+        ncclResult_t r5 = g_nccl.GroupEnd();
+        for (ncclResult_t x : {r1, r2, r3, r4, r5}) if (x != ncclSuccess) r = x;
+        if (r == ncclSuccess) e = cudaStreamSynchronize(c->stream);
+    }
+    if (e == cudaSuccess && r == ncclSuccess) {
+        e = cudaMemcpy(&c->peer_dn.info, dev + sizeof(PeerInfo), sizeof(PeerInfo), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(&c->peer_up.info, dev + 2 * sizeof(PeerInfo), sizeof(PeerInfo), cudaMemcpyDeviceToHost);
+    }
+    if (e != cudaSuccess || r != ncclSuccess) {
+        cudaFree(dev);
+        if (r != ncclSuccess) return fail(LBM_ERR_NCCL, "peer descriptor exchange: %s", g_nccl.GetErrorString(r));
+        return fail(LBM_ERR_CUDA, "peer descriptor exchange: %s", cudaGetErrorString(e));
+    }
+    if (local_ok) {
+        local_ok = p2p_map_one(c, c->peer_up) ? 1 : 0;
+        if (local_ok) {
+            if (c->up == c->down) { c->peer_dn.arena = c->peer_up.arena; c->peer_dn.ipc_base = nullptr; }
+            else local_ok = p2p_map_one(c, c->peer_dn) ? 1 : 0;
+        }
+    }
+    // every rank must take the same path: min over ranks
+    int *flag = reinterpret_cast<int *>(dev + 3 * sizeof(PeerInfo));
+    e = cudaMemcpy(flag, &local_ok, sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        r = g_nccl.AllReduce(flag, flag, 1, ncclInt, ncclMin, c->comm, c->stream);
+        if (r == ncclSuccess) e = cudaStreamSynchronize(c->stream);
+    }
+    int all_ok = 0;
+    if (e == cudaSuccess && r == ncclSuccess) e = cudaMemcpy(&all_ok, flag, sizeof(int), cudaMemcpyDeviceToHost);
+    cudaFree(dev);
+    if (r != ncclSuccess) return fail(LBM_ERR_NCCL, "peer agreement: %s", g_nccl.GetErrorString(r));
+    if (e != cudaSuccess) return fail(LBM_ERR_CUDA, "peer agreement: %s", cudaGetErrorString(e));
+    if (all_ok) c->p2p_on = true;
+    else p2p_unmap(c);
+    return 0;
+}
+
+// after a stream synchronisation: did a device-side wait of the protocol give up?
+static int p2p_check(lbm_ctx *c) {
+    if (!c->p2p_on || c->epoch == 0) return 0;
+    unsigned long long v = 0;
+    CU(cudaMemcpyAsync(&v, my_flags(c) + P2P_TIMEOUT, sizeof(v), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (v) return fail(LBM_ERR_STATE, "peer-memory halo exchange timed out waiting for a neighbour (epoch/token %llu)", v);
+    return 0;
+}
+
+template <typename T>
+static void fill_p2p(const lbm_ctx *c, KParams<T> &p, int dst) {
+    const size_t org = ((size_t)c->gy * c->pitch + c->gx) * c->elt;
+    p.peer_up = reinterpret_cast<T *>(c->peer_up.arena + ARENA_HDR + (size_t)dst * c->peer_up.info.buf_bytes + org);
+    p.peer_dn = reinterpret_cast<T *>(c->peer_dn.arena + ARENA_HDR + (size_t)dst * c->peer_dn.info.buf_bytes + org);
+    p.plane_up = c->peer_up.info.plane;
+    p.plane_dn = c->peer_dn.info.plane;
+    p.nyl_dn = c->peer_dn.info.nyl;
+    p.flags = my_flags(c);
+    p.flag_at_up = peer_flags(c->peer_up) + P2P_EPOCH_FROM_DOWN;
+    p.flag_at_dn = peer_flags(c->peer_dn) + P2P_EPOCH_FROM_UP;
+}
+
+// ----------------------------------------------------------------------------------------------
 // kernel sequencing
 // ----------------------------------------------------------------------------------------------
 template <typename T>
@@ -267,6 +429,17 @@ static void run_step(lbm_ctx *c, bool pull, const KParams<T> &p, long long step,
     if (!s) s = c->stream;
     if (std::is_same<T, double>::value) c->ops->step64(c->desc.collision, pull, reinterpret_cast<const KParams<double> &>(p), step, c->opt_variant, s);
     else c->ops->step32(c->desc.collision, pull, reinterpret_cast<const KParams<float> &>(p), step, c->opt_variant, s);
+    c->launches += 1;
+}
+
+// fused launch that also pushes its boundary rows into the neighbours' ghost rows
+template <typename T>
+static void run_step_p2p(lbm_ctx *c, KParams<T> &p, int dst, long long step, cudaStream_t s) {
+    fill_p2p<T>(c, p, dst);
+    p.epoch = ++c->epoch;
+    c->p2p_in_batch = true;
+    if (std::is_same<T, double>::value) c->ops->step64_p2p(c->desc.collision, reinterpret_cast<const KParams<double> &>(p), step, c->opt_variant, s);
+    else c->ops->step32_p2p(c->desc.collision, reinterpret_cast<const KParams<float> &>(p), step, c->opt_variant, s);
     c->launches += 1;
 }
 
@@ -289,7 +462,30 @@ static int do_fused(lbm_ctx *c, int src, int dst, long long step) {
     } else if (!c->opt_overlap || c->nyl < 2 * H + 1) {
         int rc = wait_comm(c);
         if (rc) return rc;
+        if (c->p2p_on && c->opt_p2p) {  // whole slab in one launch; it pushes its own boundary rows
+            run_step_p2p<T>(c, p, dst, step, c->stream);
+            CU(cudaGetLastError());
+            return 0;
+        }
         run_step<T>(c, true, p, step);
+    } else if (c->p2p_on && c->opt_p2p) {
+        // Peer-memory exchange: the boundary launch itself writes its rows into the neighbours' ghost rows and
+        // hand-shakes through flags in peer memory (kernels_inst.cu), concurrently with the interior launch:
+        //   main   : [fork] interior(t) .................. [join ev_b]
+        //   bstream: wait fork (+ a pending NCCL exchange of the batch's first state); boundary+push(t); record ev_b
+        CU(cudaEventRecord(c->ev_fork, c->stream));
+        CU(cudaStreamWaitEvent(c->bstream, c->ev_fork, 0));
+        if (c->comm_pending) { CU(cudaStreamWaitEvent(c->bstream, c->ev_c, 0)); c->comm_pending = false; }
+        KParams<T> pb = p;
+        pb.row_a0 = 0; pb.row_an = H; pb.row_b0 = c->nyl - H; pb.nrows = 2 * H;
+        run_step_p2p<T>(c, pb, dst, step, c->bstream);
+        CU(cudaEventRecord(c->ev_b, c->bstream));
+        KParams<T> pi = p;
+        pi.row_a0 = H; pi.row_an = c->nyl - 2 * H; pi.nrows = pi.row_an;
+        run_step<T>(c, true, pi, step);
+        CU(cudaGetLastError());
+        CU(cudaStreamWaitEvent(c->stream, c->ev_b, 0));  // join
+        return 0;
     } else {
         // The 2H boundary rows are the only ones that read halos and the only ones the neighbours need.
         // They run on a high-priority side stream concurrently with the interior kernel:
@@ -406,7 +602,9 @@ void lbm_destroy(lbm_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
     if (c->bstream) cudaStreamSynchronize(c->bstream);
+    p2p_unmap(c);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    if (c->arena) { cudaFree(c->arena); c->buf[0] = c->buf[1] = nullptr; }
     for (void *p : {c->buf[0], c->buf[1], c->field, c->sep_fx, c->sep_fy, (void *)c->partials, (void *)c->red_out, (void *)c->u_old})
         if (p) cudaFree(p);
     for (cudaEvent_t e : {c->ev_b, c->ev_c, c->ev_t0, c->ev_t1, c->ev_u0, c->ev_u1, c->ev_fork})
@@ -456,8 +654,9 @@ int lbm_create(const lbm_desc *d, lbm_ctx **out) {
     c->nyl = base + (d->rank < rem ? 1 : 0);
     c->y0 = d->rank * base + (d->rank < rem ? d->rank : rem);
     if (d->world > 1 && c->nyl < li.H) {
+        const int nyl = c->nyl;
         delete c;
-        return fail(LBM_ERR_INVALID, "slab of %d rows is thinner than the halo (%d)", c->nyl, li.H);
+        return fail(LBM_ERR_INVALID, "slab of %d rows is thinner than the halo (%d)", nyl, li.H);
     }
     c->elt = d->dtype == LBM_F64 ? 8 : 4;
     const int align = (int)(128 / c->elt);
@@ -482,11 +681,23 @@ int lbm_create(const lbm_desc *d, lbm_ctx **out) {
     int rc = 0;
     auto bail = [&](int code) { lbm_destroy(c); return code; };
     if (ops->init_constants() != 0) return bail(fail(LBM_ERR_CUDA, "constant upload failed: %s", cudaGetErrorString(cudaGetLastError())));
-    const size_t bytes = (size_t)li.Q * c->plane * c->elt;
-    for (int b = 0; b < 2; ++b) {
-        e = cudaMalloc(&c->buf[b], bytes);
-        if (e != cudaSuccess) return bail(fail(LBM_ERR_NOMEM, "cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString(e)));
-        cudaMemset(c->buf[b], 0, bytes);
+    const size_t bytes = ((size_t)li.Q * c->plane * c->elt + 255) / 256 * 256;
+    c->buf_bytes = bytes;
+    if (d->world > 1) {
+        // one allocation [flag block | buf 0 | buf 1] that the neighbours map (peer-memory halo exchange)
+        size_t total = ARENA_HDR + 2 * bytes;
+        if (total < ((size_t)2 << 20)) total = (size_t)2 << 20;
+        e = cudaMalloc(&c->arena, total);
+        if (e != cudaSuccess) return bail(fail(LBM_ERR_NOMEM, "cudaMalloc(%zu bytes): %s", total, cudaGetErrorString(e)));
+        cudaMemset(c->arena, 0, total);
+        c->buf[0] = (char *)c->arena + ARENA_HDR;
+        c->buf[1] = (char *)c->arena + ARENA_HDR + bytes;
+    } else {
+        for (int b = 0; b < 2; ++b) {
+            e = cudaMalloc(&c->buf[b], bytes);
+            if (e != cudaSuccess) return bail(fail(LBM_ERR_NOMEM, "cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString(e)));
+            cudaMemset(c->buf[b], 0, bytes);
+        }
     }
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -507,6 +718,9 @@ int lbm_create(const lbm_desc *d, lbm_ctx **out) {
         memcpy(&uid, d->nccl_id, sizeof(uid));
         ncclResult_t r = g_nccl.CommInitRank(&c->comm, d->world, uid, d->rank);
         if (r != ncclSuccess) return bail(fail(LBM_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString(r)));
+        cudaDeviceSynchronize();
+        rc = p2p_connect(c);
+        if (rc) return bail(rc);
     }
     cudaDeviceSynchronize();
     *out = c;
@@ -619,7 +833,8 @@ int lbm_download_f(lbm_ctx *c, double *f) {
     CU(cudaSetDevice(c->desc.device));
     int rc = materialize(c);
     if (rc) return rc;
-    return download_buffer(c, c->cur, f);
+    rc = download_buffer(c, c->cur, f);
+    return rc ? rc : p2p_check(c);
 }
 
 int lbm_download_f_collision(lbm_ctx *c, double *f) {
@@ -844,11 +1059,25 @@ int lbm_step(lbm_ctx *c, int64_t t0, int64_t nsteps, double dt) {
     int rc = check_force_window(c, t0, nsteps);
     if (rc) return rc;
     CU(cudaEventRecord(c->ev_t0, c->stream));
+    c->p2p_in_batch = false;
+    if (c->p2p_on && c->opt_p2p) {
+        // neighbour barrier: everything any of us enqueued before this batch (downloads, diagnostics, NCCL
+        // exchanges) is finished before the first peer store of the batch
+        ++c->batch;
+        c->ops->p2p_barrier(my_flags(c), peer_flags(c->peer_up) + P2P_BATCH_FROM_DOWN, peer_flags(c->peer_dn) + P2P_BATCH_FROM_UP,
+                            c->batch, c->stream);
+        c->launches += 1;
+    }
     rc = is64(c) ? do_steps<double>(c, t0, nsteps) : do_steps<float>(c, t0, nsteps);
     if (rc) return rc;
     if (c->desc.world > 1) {
         rc = wait_comm(c);  // the batch ends when the last halo has landed
         if (rc) return rc;
+        if (c->p2p_in_batch) {
+            c->ops->p2p_wait_epoch(my_flags(c), c->epoch, c->stream);
+            c->launches += 1;
+            CU(cudaGetLastError());
+        }
     }
     CU(cudaEventRecord(c->ev_t1, c->stream));
     c->timed = true;
@@ -861,7 +1090,7 @@ int lbm_sync(lbm_ctx *c) {
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaStreamSynchronize(c->bstream));
     CU(cudaStreamSynchronize(c->comm_stream));
-    return 0;
+    return p2p_check(c);
 }
 
 int lbm_last_step_ms(lbm_ctx *c, float *ms) {
@@ -886,15 +1115,17 @@ int lbm_timer_stop(lbm_ctx *c, float *ms) {
     CU(cudaEventRecord(c->ev_u1, c->stream));
     CU(cudaEventSynchronize(c->ev_u1));
     CU(cudaEventElapsedTime(ms, c->ev_u0, c->ev_u1));
-    return 0;
+    return p2p_check(c);
 }
 
 int64_t lbm_kernel_launches(const lbm_ctx *c) { return c ? c->launches : 0; }
+int lbm_halo_path(const lbm_ctx *c) { return !c || c->desc.world == 1 ? 0 : (c->p2p_on && c->opt_p2p ? 2 : 1); }
 
 int lbm_set_option(lbm_ctx *c, const char *key, int64_t value) {
     if (!c || !key) return fail(LBM_ERR_INVALID, "null argument");
     if (!strcmp(key, "variant")) c->opt_variant = (int)value;
     else if (!strcmp(key, "overlap")) c->opt_overlap = (int)value;
+    else if (!strcmp(key, "p2p")) c->opt_p2p = (int)value;
     else return fail(LBM_ERR_INVALID, "unknown option '%s'", key);
     return 0;
 }

@@ -126,7 +126,7 @@ __device__ __forceinline__ void load_pair(const KParams<float> &p, int x0, int y
     }
 }
 
-template <int CM, bool PULL, int MINB>
+template <int CM, bool PULL, int MINB, bool P2P = false>
 __global__ void __launch_bounds__(256, MINB) k_step_x2(const __grid_constant__ KParams<float> p, long long step) {
     const int x0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
     // Whole warps stay alive for the shuffles; out-of-range lanes work on x = 0 and skip the store.
@@ -134,6 +134,7 @@ __global__ void __launch_bounds__(256, MINB) k_step_x2(const __grid_constant__ K
     // from its right neighbour (the first out-of-range lane), so no special case is needed there.
     const bool valid = x0 < p.nx;
     const int xl = valid ? x0 : 0;
+    if constexpr (P2P) p2p_wait(p);
     const LatConst<float> &c = c_lat32;
     X2Consts k;
     k.cs = f2(c.css); k.half = f2(0.5f); k.sixth = f2(1.0f / 6); k.t24 = f2(1.0f / 24); k.m3 = f2(-3.0f);
@@ -208,14 +209,21 @@ __global__ void __launch_bounds__(256, MINB) k_step_x2(const __grid_constant__ K
         if (valid) {
             store_images(p, xl, y);
             store_images(p, xl + 1, y);
+            if constexpr (P2P) {
+                if (y < H || y >= p.nyl - H) {
+                    p2p_store(p, xl, y);
+                    p2p_store(p, xl + 1, y);
+                }
+            }
         }
     }
+    if constexpr (P2P) p2p_signal(p);
 }
 
-template <int CM, bool PULL, int MINB>
+template <int CM, bool PULL, int MINB, bool P2P = false>
 static void launch_step_x2(const KParams<float> &p, long long step, cudaStream_t s) {
     const int pairs = p.nx / 2;
     dim3 block; pick_block(pairs, block);
     dim3 grid = grid_for(p, block, p.nrows, pairs);
-    k_step_x2<CM, PULL, MINB><<<grid, block, 0, s>>>(p, step);
+    k_step_x2<CM, PULL, MINB, P2P><<<grid, block, 0, s>>>(p, step);
 }

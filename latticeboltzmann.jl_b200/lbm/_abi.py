@@ -36,7 +36,7 @@ EXPORTS = [
     "lbm_set_force_none", "lbm_set_force_uniform", "lbm_set_force_field", "lbm_set_force_separable",
     "lbm_collide", "lbm_stream", "lbm_apply_bcs", "lbm_step", "lbm_sync", "lbm_moments", "lbm_reduce",
     "lbm_reduce_errors",
-    "lbm_kernel_launches", "lbm_last_step_ms", "lbm_timer_start", "lbm_timer_stop", "lbm_set_option",
+    "lbm_kernel_launches", "lbm_halo_path", "lbm_last_step_ms", "lbm_timer_start", "lbm_timer_stop", "lbm_set_option",
 ]
 
 
@@ -111,6 +111,7 @@ def lib():
     l.lbm_reduce_errors.argtypes = [vp, C.c_double, C.c_double, C.POINTER(lbm_sep_field), dp]
     l.lbm_kernel_launches.argtypes = [vp]
     l.lbm_kernel_launches.restype = C.c_int64
+    l.lbm_halo_path.argtypes = [vp]
     l.lbm_last_step_ms.argtypes = [vp, C.POINTER(C.c_float)]
     l.lbm_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     l.lbm_timer_start.argtypes = [vp]
@@ -332,6 +333,11 @@ class Context:
     @property
     def kernel_launches(self):
         return int(lib().lbm_kernel_launches(self._h))
+
+    @property
+    def halo_path(self):
+        """0 single GPU, 1 NCCL send/recv, 2 peer-memory stores from the boundary-row launch."""
+        return int(lib().lbm_halo_path(self._h))
 
     def last_step_ms(self):
         ms = C.c_float()

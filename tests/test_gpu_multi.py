@@ -1,5 +1,6 @@
-"""y-slab multi-GPU parity: two ranks (one process per GPU, halos exchanged by liblbm_b200.so over
-NCCL) must reproduce the single-domain oracle bit for bit."""
+"""y-slab multi-GPU parity: the ranks (one process per GPU; halos pushed into the neighbours' ghost rows through
+peer memory by the boundary-row launch, or exchanged with NCCL send/recv) must reproduce the single-domain oracle
+bit for bit."""
 import os
 
 import numpy as np
@@ -8,7 +9,7 @@ import pytest
 pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
 
 
-def _worker(rank, world, idq, out, lattice, model, nx, ny, nsteps, walls, dtype, overlap):
+def _worker(rank, world, idq, out, lattice, model, nx, ny, nsteps, walls, dtype, overlap, p2p=1, single_steps=False):
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, root)
@@ -34,30 +35,36 @@ def _worker(rank, world, idq, out, lattice, model, nx, ny, nsteps, walls, dtype,
                    lbm.MovingWall(lbm.North(), (1, nx), (1, ny), [0.01, 0.0]).to_abi()]
         c = _abi.Context(nx, ny, lattice, code, taus, bcs, dtype=dtype, device=rank, rank=rank, world=world, nccl_id=nid)
         c.set_option("overlap", overlap)
+        c.set_option("p2p", p2p)
+        path = c.halo_path
         assert (c.y0, c.ny_local) == lbm.slab_rows(ny, rank, world)
         c.set_force_uniform(1e-6, 2e-6)
         slab = np.asfortranarray(np.transpose(f[:, c.y0:c.y0 + c.ny_local], (2, 1, 0)))
         c.upload_f(slab)
-        c.step(0, 3)
-        c.step(3, nsteps - 3)
+        if single_steps:  # one batch per step: exercises the batch barrier / final-epoch wait every step
+            for t in range(nsteps):
+                c.step(t, 1)
+        else:
+            c.step(0, 3)
+            c.step(3, nsteps - 3)
         got = np.transpose(c.download_f(), (2, 1, 0))
         red = c.reduce(_abi.REDUCE_CONSERVED)
         c.step(nsteps, 2)  # resume path after a download
         got2 = np.transpose(c.download_f(), (2, 1, 0))
-        out.put((rank, c.y0, got, got2, red, None))
+        out.put((rank, c.y0, got, got2, red, None, path))
         c.close()
     except Exception as e:  # pragma: no cover
-        out.put((rank, -1, None, None, None, repr(e)))
+        out.put((rank, -1, None, None, None, repr(e), -1))
 
 
-@pytest.mark.parametrize("lattice,model,walls,overlap", [
-    ("D2Q9", "TRT", False, 1), ("D2Q9", "TRT", True, 1), ("D2Q9", "SRT", True, 0),
-    ("D2Q13", "TRT", False, 1), ("D2Q37", "TRT", True, 1), ("D2Q37", "MRT", False, 1), ("D2Q17", "SRT", False, 1),
-])
-def test_two_slabs_equal_single_domain(lattice, model, walls, overlap):
+def _gpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+def _run_slabs(lattice, model, walls, overlap, p2p, world=2, nx=40, ny=37, nsteps=9, single_steps=False):
     import torch.multiprocessing as mp
     import oracle.lbm_oracle as O
-    nx, ny, nsteps, world = 40, 37, 9, 2
     qo = O.L.BY_NAME[lattice]()
     rng = np.random.default_rng(5)
     f = np.stack([qo.w[i] * (1 + 0.01 * rng.uniform(-1, 1, (ny, nx))) for i in range(qo.Q)])
@@ -72,7 +79,8 @@ def test_two_slabs_equal_single_domain(lattice, model, walls, overlap):
         want2, _ = O.step(cm, qo, bcs, want2)
     ctx = mp.get_context("spawn")
     idq, out = ctx.Queue(), ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, idq, out, lattice, model, nx, ny, nsteps, walls, 0, overlap))
+    procs = [ctx.Process(target=_worker, args=(r, world, idq, out, lattice, model, nx, ny, nsteps, walls, 0, overlap, p2p,
+                                               single_steps))
              for r in range(world)]
     for p in procs:
         p.start()
@@ -80,8 +88,10 @@ def test_two_slabs_equal_single_domain(lattice, model, walls, overlap):
     for p in procs:
         p.join(timeout=60)
     mass = 0.0
-    for rank, y0, got, got2, red, err in res:
+    paths = set()
+    for rank, y0, got, got2, red, err, path in res:
         assert err is None, err
+        paths.add(path)
         nyl = got.shape[1]
         if model == "MRT":
             assert np.abs(got - want[:, y0:y0 + nyl]).max() < 1e-13
@@ -91,3 +101,40 @@ def test_two_slabs_equal_single_domain(lattice, model, walls, overlap):
             assert np.array_equal(got2, want2[:, y0:y0 + nyl]), f"rank {rank} (resume)"
         mass += red[0]
     assert np.isclose(mass, O.density(qo, [want[i] for i in range(qo.Q)]).sum(), rtol=1e-13)
+    assert len(paths) == 1, f"ranks disagree on the halo path: {paths}"
+    if not p2p:
+        assert paths == {1}
+    return paths.pop()
+
+
+@pytest.mark.parametrize("lattice,model,walls,overlap,p2p", [
+    ("D2Q9", "TRT", False, 1, 1), ("D2Q9", "TRT", True, 1, 1), ("D2Q9", "SRT", True, 0, 1),
+    ("D2Q13", "TRT", False, 1, 1), ("D2Q37", "TRT", True, 1, 1), ("D2Q37", "MRT", False, 1, 1), ("D2Q17", "SRT", False, 1, 1),
+    # NCCL send/recv path (LBM_P2P=0 / boxes without peer access)
+    ("D2Q9", "TRT", True, 1, 0), ("D2Q9", "SRT", True, 0, 0), ("D2Q37", "TRT", True, 1, 0),
+])
+def test_two_slabs_equal_single_domain(lattice, model, walls, overlap, p2p):
+    _run_slabs(lattice, model, walls, overlap, p2p)
+
+
+def test_peer_memory_path_is_taken_on_nvlink_boxes():
+    """On the B200 boxes (NVSwitch, every GPU can map every peer) the default halo path must be peer memory."""
+    assert _run_slabs("D2Q9", "TRT", False, 1, 1) == 2
+
+
+@pytest.mark.parametrize("lattice,model,walls,nx,ny,nsteps,single_steps", [
+    ("D2Q9", "TRT", False, 1024, 203, 60, False),   # many CTAs per boundary launch, uneven slabs
+    ("D2Q9", "SRT", True, 300, 64, 40, True),       # one batch per step
+    ("D2Q37", "TRT", True, 515, 47, 24, False),     # halo 3, odd width
+    ("D2Q21", "TRT", False, 64, 13, 12, True),      # thin slabs (6/7 rows <= 2H+1 on one rank): single-launch path
+])
+def test_peer_memory_stress(lattice, model, walls, nx, ny, nsteps, single_steps):
+    _run_slabs(lattice, model, walls, 1, 1, nx=nx, ny=ny, nsteps=nsteps, single_steps=single_steps)
+
+
+@pytest.mark.parametrize("world", [3, 4, 8])
+@pytest.mark.parametrize("lattice,model,walls", [("D2Q9", "TRT", True), ("D2Q37", "TRT", False)])
+def test_more_slabs(world, lattice, model, walls):
+    if _gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    _run_slabs(lattice, model, walls, 1, 1, world=world, nx=136, ny=16 * world + 5, nsteps=15)
