@@ -60,6 +60,7 @@ def parse():
     ap.add_argument("--config", default="C2", choices=["C2", "C3", "C4", "C5s", "C5w"],
                     help="BASELINE.json config preset (C2 = default bench workload; see build_case)")
     ap.add_argument("--p2p", type=int, default=1, help="N > 1: 1 = peer-memory halo stores (default), 0 = NCCL send/recv")
+    ap.add_argument("--graph", type=int, default=1, help="1 = replay CUDA graphs of 16 fused steps (default), 0 = plain launches")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-n", type=int, default=1024)
@@ -247,6 +248,7 @@ def run_b200(a):
     ctx = lbm.model.make_context(q, cm, problem.boundary_conditions(), nx, ny, a.dtype, a.arith, comm, local)
     ctx.set_option("variant", a.variant)
     ctx.set_option("p2p", a.p2p)
+    ctx.set_option("graph", a.graph)
     halo_path = {0: "none (single GPU)", 1: "NCCL send/recv on a side stream", 2: "peer-memory stores from the boundary-row launch"}[ctx.halo_path]
     nyl = ctx.ny_local
     state = lbm.DeviceState(ctx, q, cm, comm)
@@ -346,7 +348,7 @@ def run_b200(a):
             "dtype": a.dtype, "data": "synthetic",
             "config": {"workload": case["workload"], "preset": a.config,
                        "grid_per_gpu": [nx, nyl], "grid_global": [nx, ny], "lattice_steps_per_bench_step": inner,
-                       "arith": a.arith, "variant": a.variant, "parallelism": f"y-slabs x{world}", "halo_exchange": halo_path,
+                       "arith": a.arith, "variant": a.variant, "cuda_graphs": bool(a.graph), "parallelism": f"y-slabs x{world}", "halo_exchange": halo_path,
                        "l2": "working set (2 x %.2f GB per GPU) >> 126 MB L2; no flush needed" % (nx * nyl * q.Q * BYTES[a.dtype] / 1e9),
                        "wall_ms_per_step": region_ms / a.steps},
             "clocks": clocks,

@@ -48,7 +48,11 @@ typedef enum {
 typedef enum { LBM_D2Q4 = 0, LBM_D2Q5, LBM_D2Q9, LBM_D2Q13, LBM_D2Q17, LBM_D2Q21, LBM_D2Q37, LBM_NUM_LATTICES } lbm_lattice;
 typedef enum { LBM_F64 = 0, LBM_F32 = 1 } lbm_dtype;
 /* src/collision_models/{srt,trt,mrt}.jl */
-typedef enum { LBM_SRT = 0, LBM_TRT = 1, LBM_MRT = 2 } lbm_collision;
+/* LBM_ITERATIVE_INIT: IterativeInitializationCollisionModel (collision_models/iterative_initialization.jl:1-60), the
+ * constant-velocity SRT operator of the Mei et al. initialisation (initial_conditions/mei_et_al.jl:11-40):
+ * f_out = (1 - 1/tau) f + (1/tau) (w_i rho + w_i (css c.u0 + (css^2 (c.u0)^2 - css u0.u0) / 2)), rho = sum(f), with the
+ * prescribed lattice velocity u0(x, y) given by lbm_set_velocity_field.  tau[0] = tau. */
+typedef enum { LBM_SRT = 0, LBM_TRT = 1, LBM_MRT = 2, LBM_ITERATIVE_INIT = 3 } lbm_collision;
 /* 0: reference operation order, no FMA contraction (bit-comparable with the oracle in Float64)
  * 1: FMA contraction + algebraic simplification allowed */
 typedef enum { LBM_ARITH_EXACT = 0, LBM_ARITH_FAST = 1 } lbm_arith;
@@ -132,6 +136,9 @@ int lbm_set_force_none(lbm_ctx *ctx);
 int lbm_set_force_uniform(lbm_ctx *ctx, double fx, double fy);
 /* static per-node field F[2][ny_local][nx] */
 int lbm_set_force_field(lbm_ctx *ctx, const double *F);
+/* LBM_ITERATIVE_INIT: the velocity u0[2][ny_local][nx] (lattice units) every node is held at -- `lattice_velocity(q,
+ * problem, x, y)` of iterative_initialization.jl:26, from which the kernel evaluates the operator's `nonlinear_term`. */
+int lbm_set_velocity_field(lbm_ctx *ctx, const double *u0);
 /* time-dependent separable force for steps t0 .. t0+nsteps-1:
  * F_x(x, y, t) = fx_of_y[t - t0][y],  F_y(x, y, t) = fy_of_x[t - t0][x]
  * (DecayingShearFlow, problems/decaying_shear_flow.jl:131-147). */
@@ -167,7 +174,13 @@ typedef enum {
     LBM_REDUCE_VELOCITY_CHANGE = 1,
     /* out[0] = sum rho, out[1] = sum rho*(ux+uy), out[2] = sum rho*(ux^2+uy^2) in lattice units
      * (track_hydrodynamic_errors.jl:200-202 before unit scaling) */
-    LBM_REDUCE_CONSERVED = 2
+    LBM_REDUCE_CONSERVED = 2,
+    /* out[0] = sum (rho - rho_old)^2 over the local nodes, out[1] = rho at the global node (NX, NY) (0 on ranks that do
+     * not own it), then rho_old := rho (rho_old starts at 0).  DensityConvergence
+     * (stopping_criteria/density_convergence.jl:6-17) evaluates norm(rho - rho_old) -- but its loop `for x_idx in nx,
+     * y_idx in ny` (:9) visits only the node (NX, NY), so the reference's criterion is |out[1] - previous out[1]|;
+     * out[0] is the norm it evidently intended. */
+    LBM_REDUCE_DENSITY_CHANGE = 3
 } lbm_reduce_kind;
 /* Local (per-rank) partial sums; the host adds ranks. */
 int lbm_reduce(lbm_ctx *ctx, int32_t kind, double *out, int32_t n);

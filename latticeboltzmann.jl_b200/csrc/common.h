@@ -26,6 +26,7 @@ enum {
     P2P_CTA_COUNT = 3,        // CTAs of the running boundary launch that have finished
     P2P_BATCH_FROM_DOWN = 4,  // lbm_step batch tokens
     P2P_BATCH_FROM_UP = 5,
+    P2P_EPOCH_BASE = 6,       // epoch of the state a replayed CUDA graph starts from (set before each replay)
     P2P_MAGIC = 7,            // written at create time; read through the mapping by the neighbours as a self-check
     P2P_NFLAGS = 8
 };
@@ -71,7 +72,8 @@ struct KParams {
     unsigned long long *flags;          // local flag block, slots P2P_*
     unsigned long long *flag_at_up;     // up neighbour's flags[P2P_EPOCH_FROM_DOWN]  (I am its `down`)
     unsigned long long *flag_at_dn;     // down neighbour's flags[P2P_EPOCH_FROM_UP]  (I am its `up`)
-    unsigned long long epoch;           // sequence number of the state this launch produces
+    unsigned long long epoch;           // sequence number of the state this launch produces ...
+    const unsigned long long *epoch_base;  // ... plus *epoch_base when set (launches replayed from a CUDA graph)
     // boundary conditions
     int nbc;
     int bc_sides;  // bit d set: some boundary condition faces direction d (lbm_direction) -> only those edges take the BC path
@@ -116,6 +118,7 @@ struct Ops {
     void (*step32_p2p)(int cm, const KParams<float> &p, long long step, int variant, cudaStream_t s);
     void (*p2p_barrier)(unsigned long long *flags, unsigned long long *at_up, unsigned long long *at_dn, unsigned long long token, cudaStream_t s);
     void (*p2p_wait_epoch)(unsigned long long *flags, unsigned long long need, cudaStream_t s);
+    void (*p2p_set_base)(unsigned long long *flags, unsigned long long base, cudaStream_t s);
     // periodic pull (+ BCs when p.nbc > 0) without collision
     void (*stream64)(const KParams<double> &p, cudaStream_t s);
     void (*stream32)(const KParams<float> &p, cudaStream_t s);

@@ -329,6 +329,23 @@ template <int CM, typename T, class Emit>
 __device__ __forceinline__ void collide_node(const KParams<T> &p, const T (&f)[Q], bool forced, T Fx, T Fy, Emit &&emit) {
     T rho, ux, uy, drho;
     rho_u(f, rho, ux, uy, drho);
+    if constexpr (CM == LBM_ITERATIVE_INIT) {
+        // iterative_initialization.jl:42-60: the node keeps the prescribed velocity u0 = (Fx, Fy); only rho comes from f.
+        // nonlinear_term (:21-35) = w_i rho_0 (a_H_1 + a_H_2 / 2), rho_0 = 1, is evaluated here instead of being stored.
+        const LatConst<T> &c = LC<T>();
+        const T cs = c.css;
+        const T u2 = Fx * Fx + Fy * Fy;
+        static_for<0, Q>([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            const T udx = cdot<L::cx(i), L::cy(i)>(Fx, Fy);
+            const T a1 = cs * udx;
+            const T a2 = (cs * cs) * (udx * udx) - cs * u2;
+            const T nl = c.w[i] * (a1 + a2 / T(2));
+            const T feq = c.w[i] * (Shifted<T>::value ? drho : rho) + nl;  // shifted storage: feq - w
+            emit(I, p.c[0] * f[i] + p.c[1] * feq);
+        });
+        return;
+    }
     if (forced) {  // equilibrium velocity shift u + tau F (srt.jl:54, trt.jl:79, mrt.jl:94)
         ux = ux + p.shift * Fx;
         uy = uy + p.shift * Fy;
@@ -494,8 +511,13 @@ __device__ __noinline__ void p2p_spin(unsigned long long *flags, int a, int b, u
 }
 
 template <typename T>
+__device__ __forceinline__ unsigned long long p2p_epoch(const KParams<T> &p) {
+    return p.epoch + (p.epoch_base ? *p.epoch_base : 0ULL);
+}
+
+template <typename T>
 __device__ __forceinline__ void p2p_wait(const KParams<T> &p) {
-    if (threadIdx.x == 0 && threadIdx.y == 0) p2p_spin(p.flags, P2P_EPOCH_FROM_DOWN, P2P_EPOCH_FROM_UP, p.epoch - 1, 10000000000ULL);
+    if (threadIdx.x == 0 && threadIdx.y == 0) p2p_spin(p.flags, P2P_EPOCH_FROM_DOWN, P2P_EPOCH_FROM_UP, p2p_epoch(p) - 1, 10000000000ULL);
     __syncthreads();
 }
 
@@ -544,8 +566,9 @@ __device__ __forceinline__ void p2p_signal(const KParams<T> &p) {
         if (atomicAdd(p.flags + P2P_CTA_COUNT, 1ULL) == total - 1) {
             p.flags[P2P_CTA_COUNT] = 0;
             __threadfence_system();
-            st_release_sys(p.flag_at_up, p.epoch);
-            st_release_sys(p.flag_at_dn, p.epoch);
+            const unsigned long long e = p2p_epoch(p);
+            st_release_sys(p.flag_at_up, e);
+            st_release_sys(p.flag_at_dn, e);
         }
     }
 }
@@ -563,6 +586,7 @@ __global__ void k_p2p_barrier(unsigned long long *flags, unsigned long long *at_
 __global__ void k_p2p_wait_epoch(unsigned long long *flags, unsigned long long need) {
     p2p_spin(flags, P2P_EPOCH_FROM_DOWN, P2P_EPOCH_FROM_UP, need, 10000000000ULL);
 }
+__global__ void k_p2p_set_base(unsigned long long *flags, unsigned long long base) { flags[P2P_EPOCH_BASE] = base; }
 
 // ------------------------------------------------------------------------------------------
 // K1/K2: collide, optionally fused with the pull (stream + BCs) of the previous step
@@ -737,6 +761,11 @@ __global__ void __launch_bounds__(256) k_reduce(const __grid_constant__ KParams<
                 acc[0] += ((ux - ox) * (ux - ox) + (uy - oy) * (uy - oy));
                 acc[1] += ox * ox + oy * oy;
                 ra.u_old[n] = ux; ra.u_old[N + n] = uy;
+            } else if (ra.kind == LBM_REDUCE_DENSITY_CHANGE) {
+                const double o = ra.u_old[n];
+                acc[0] += (rho - o) * (rho - o);
+                if (x == p.nx - 1 && p.y0g + y == p.nyg - 1) acc[1] += rho;
+                ra.u_old[n] = rho;
             } else {
                 acc[0] += rho; acc[1] += rho * (ux + uy); acc[2] += rho * (ux * ux + uy * uy);
             }
@@ -962,7 +991,7 @@ static void launch_step_impl(int cm, bool pull, const KParams<T> &p, long long s
     if constexpr (LBM_FAST && std::is_same<T, float>::value) {
         // Float32 fast mode: packed two-nodes-per-thread kernel (variant 99 forces the scalar one)
         // (measured faster for Q <= 13; the wide lattices run out of registers with 64-bit pairs -- variant 98 forces it)
-        if (((Q <= 13 && variant != 99) || variant == 98) && cm != LBM_MRT && p.nx % 2 == 0 && p.nx >= 2) {
+        if (((Q <= 13 && variant != 99) || variant == 98) && (cm == LBM_SRT || cm == LBM_TRT) && p.nx % 2 == 0 && p.nx >= 2) {
             if constexpr (P2P) {
                 if (cm == LBM_SRT) launch_step_x2<LBM_SRT, true, X2_MINB, true>(p, step, s);
                 else launch_step_x2<LBM_TRT, true, X2_MINB, true>(p, step, s);
@@ -985,7 +1014,8 @@ static void launch_step_impl(int cm, bool pull, const KParams<T> &p, long long s
         switch (cm) {
         case LBM_SRT: LBM_LAUNCH_P2P(LBM_SRT) break;
         case LBM_TRT: LBM_LAUNCH_P2P(LBM_TRT) break;
-        default: LBM_LAUNCH_P2P(LBM_MRT) break;
+        case LBM_MRT: LBM_LAUNCH_P2P(LBM_MRT) break;
+        default: LBM_LAUNCH_P2P(LBM_ITERATIVE_INIT) break;
         }
 #undef LBM_LAUNCH_P2P
         return;
@@ -1009,7 +1039,8 @@ static void launch_step_impl(int cm, bool pull, const KParams<T> &p, long long s
     switch (cm) {
     case LBM_SRT: LBM_LAUNCH(LBM_SRT) break;
     case LBM_TRT: LBM_LAUNCH(LBM_TRT) break;
-    default: LBM_LAUNCH(LBM_MRT) break;
+    case LBM_MRT: LBM_LAUNCH(LBM_MRT) break;
+    default: LBM_LAUNCH(LBM_ITERATIVE_INIT) break;
     }
 #undef LBM_LAUNCH
 }
@@ -1028,6 +1059,9 @@ static void launch_p2p_barrier(unsigned long long *flags, unsigned long long *at
 }
 static void launch_p2p_wait_epoch(unsigned long long *flags, unsigned long long need, cudaStream_t s) {
     k_p2p_wait_epoch<<<1, 1, 0, s>>>(flags, need);
+}
+static void launch_p2p_set_base(unsigned long long *flags, unsigned long long base, cudaStream_t s) {
+    k_p2p_set_base<<<1, 1, 0, s>>>(flags, base);
 }
 
 template <typename T>
@@ -1100,7 +1134,7 @@ static const Ops ops = {
     LBM_LATTICE, LBM_FAST,
     &launch_step<double>, &launch_step<float>,
     &launch_step_p2p<double>, &launch_step_p2p<float>,
-    &launch_p2p_barrier, &launch_p2p_wait_epoch,
+    &launch_p2p_barrier, &launch_p2p_wait_epoch, &launch_p2p_set_base,
     &launch_stream<double>, &launch_stream<float>,
     &launch_bcs<double>, &launch_bcs<float>,
     &launch_ghosts<double>, &launch_ghosts<float>,

@@ -158,6 +158,13 @@ struct lbm_ctx {
     int opt_p2p = 1;           // lbm_set_option("p2p", 0) falls back to NCCL send/recv (same on all ranks)
     unsigned long long epoch = 0, batch = 0;
     bool p2p_in_batch = false; // a P2P launch ran in the current lbm_step batch
+    // CUDA graphs of GRAPH_STEPS fused steps (launch-bound small slabs): one per source buffer, rebuilt when
+    // anything baked into the kernel parameters changes (force data, options)
+    cudaGraphExec_t graph[2] = {nullptr, nullptr};
+    long long graph_launches[2] = {0, 0};  // kernels inside each graph
+    int opt_graph = 1;
+    bool capturing = false;
+    unsigned long long cap_rel = 0;        // relative epoch of the launch being captured
     long long launches = 0;
     bool timed = false;
     int opt_variant = 0;
@@ -193,6 +200,7 @@ static KParams<T> make_params(const lbm_ctx *c, int src, int dst) {
     const double css = c->li.css;
     switch (c->desc.collision) {
     case LBM_SRT:
+    case LBM_ITERATIVE_INIT:
         p.c[0] = (T)(1 - 1 / tau[0]); p.c[1] = (T)(1 / tau[0]); p.shift = (T)tau[0];
         break;
     case LBM_TRT:
@@ -436,8 +444,13 @@ static void run_step(lbm_ctx *c, bool pull, const KParams<T> &p, long long step,
 template <typename T>
 static void run_step_p2p(lbm_ctx *c, KParams<T> &p, int dst, long long step, cudaStream_t s) {
     fill_p2p<T>(c, p, dst);
-    p.epoch = ++c->epoch;
-    c->p2p_in_batch = true;
+    if (c->capturing) {  // replayed launches: epoch relative to the base the host sets before each replay
+        p.epoch = ++c->cap_rel;
+        p.epoch_base = my_flags(c) + P2P_EPOCH_BASE;
+    } else {
+        p.epoch = ++c->epoch;
+        c->p2p_in_batch = true;
+    }
     if (std::is_same<T, double>::value) c->ops->step64_p2p(c->desc.collision, reinterpret_cast<const KParams<double> &>(p), step, c->opt_variant, s);
     else c->ops->step32_p2p(c->desc.collision, reinterpret_cast<const KParams<float> &>(p), step, c->opt_variant, s);
     c->launches += 1;
@@ -535,11 +548,66 @@ static int do_materialize(lbm_ctx *c) {
 
 static int materialize(lbm_ctx *c) { return is64(c) ? do_materialize<double>(c) : do_materialize<float>(c); }
 
+// ----------------------------------------------------------------------------------------------
+// CUDA graphs for the step loop
+// ----------------------------------------------------------------------------------------------
+static const int GRAPH_STEPS = 16;  // even: the buffer roles return to where they started
+
+static void drop_graphs(lbm_ctx *c) {
+    for (int b = 0; b < 2; ++b)
+        if (c->graph[b]) { cudaGraphExecDestroy(c->graph[b]); c->graph[b] = nullptr; }
+}
+
+// Everything baked into a captured launch must be replay-invariant: no per-step force table, and the halo
+// exchange either absent or done by the kernels themselves (peer memory).
+static bool graph_ok(const lbm_ctx *c) {
+    return c->opt_graph && c->force_mode != 3 && (c->desc.world == 1 || (c->p2p_on && c->opt_p2p));
+}
+
+// capture GRAPH_STEPS fused steps starting from post-collision populations in buf[src]
+template <typename T>
+static int build_graph(lbm_ctx *c, int src) {
+    const long long l0 = c->launches;
+    if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); return -1; }
+    c->capturing = true;
+    c->cap_rel = 0;
+    int rc = 0, s = src;
+    for (int g = 0; g < GRAPH_STEPS && rc == 0; ++g, s = 1 - s) rc = do_fused<T>(c, s, 1 - s, 0);
+    c->capturing = false;
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+    const long long inside = c->launches - l0;
+    c->launches = l0;
+    if (rc != 0 || e != cudaSuccess || !graph) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return -1; }
+    e = cudaGraphInstantiate(&c->graph[src], graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { c->graph[src] = nullptr; cudaGetLastError(); return -1; }
+    c->graph_launches[src] = inside;
+    return 0;
+}
+
 template <typename T>
 static int do_steps(lbm_ctx *c, long long t0, long long n) {
     for (long long k = 0; k < n; ++k) {
         const long long t = t0 + k;
         int rc;
+        if (c->state == ST_COLLIDED && !c->comm_pending && n - k >= GRAPH_STEPS && graph_ok(c)) {
+            const int src = c->cur;
+            if (!c->graph[src] && build_graph<T>(c, src) != 0) {
+                c->opt_graph = 0;  // capture not possible here: plain launches from now on
+            } else {
+                if (c->desc.world > 1) {
+                    c->ops->p2p_set_base(my_flags(c), c->epoch, c->stream);
+                    c->launches += 1;
+                    c->epoch += GRAPH_STEPS;
+                    c->p2p_in_batch = true;
+                }
+                CU(cudaGraphLaunch(c->graph[src], c->stream));
+                c->launches += c->graph_launches[src];
+                k += GRAPH_STEPS - 1;
+                continue;
+            }
+        }
         if (c->state == ST_STREAM) {
             if (c->resume_ok && c->have_coll) {
                 // buf[1-cur] = f_collision of the previous step with valid ghosts: pull from it
@@ -602,6 +670,7 @@ void lbm_destroy(lbm_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
     if (c->bstream) cudaStreamSynchronize(c->bstream);
+    drop_graphs(c);
     p2p_unmap(c);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     if (c->arena) { cudaFree(c->arena); c->buf[0] = c->buf[1] = nullptr; }
@@ -623,9 +692,9 @@ int lbm_create(const lbm_desc *d, lbm_ctx **out) {
     LatticeInfo li;
     if (!lattice_info(d->lattice, li)) return fail(LBM_ERR_INVALID, "unknown lattice id %d", d->lattice);
     if (d->dtype != LBM_F64 && d->dtype != LBM_F32) return fail(LBM_ERR_INVALID, "dtype %d", d->dtype);
-    if (d->collision < LBM_SRT || d->collision > LBM_MRT) return fail(LBM_ERR_INVALID, "collision %d", d->collision);
+    if (d->collision < LBM_SRT || d->collision > LBM_ITERATIVE_INIT) return fail(LBM_ERR_INVALID, "collision %d", d->collision);
     if (d->arith != LBM_ARITH_EXACT && d->arith != LBM_ARITH_FAST) return fail(LBM_ERR_INVALID, "arith %d", d->arith);
-    const int need_tau = d->collision == LBM_SRT ? 1 : (d->collision == LBM_TRT ? 2 : li.N);
+    const int need_tau = d->collision == LBM_TRT ? 2 : (d->collision == LBM_MRT ? li.N : 1);
     if (d->ntau < need_tau || d->ntau > LBM_MAX_TAU) return fail(LBM_ERR_INVALID, "ntau %d (need >= %d)", d->ntau, need_tau);
     for (int i = 0; i < d->ntau; ++i)
         if (!(d->tau[i] == d->tau[i]) || d->tau[i] == 0.0) return fail(LBM_ERR_INVALID, "tau[%d] = %g", i, d->tau[i]);
@@ -924,6 +993,7 @@ int lbm_download_f_rows(lbm_ctx *c, int32_t y0, int32_t ny, double *f_rows) {
 
 static void free_force(lbm_ctx *c) {
     cudaStreamSynchronize(c->stream);
+    drop_graphs(c);
     for (void **p : {&c->field, &c->sep_fx, &c->sep_fy})
         if (*p) { cudaFree(*p); *p = nullptr; }
     c->force_mode = 0;
@@ -953,6 +1023,7 @@ int lbm_set_force_uniform(lbm_ctx *c, double fx, double fy) {
     if (!c) return fail(LBM_ERR_INVALID, "null context");
     CU(cudaSetDevice(c->desc.device));
     if (c->desc.collision == LBM_MRT && c->desc.ntau < 2) return fail(LBM_ERR_INVALID, "MRT forcing needs tau[1] (mrt.jl:94)");
+    if (c->desc.collision == LBM_ITERATIVE_INIT) return fail(LBM_ERR_UNSUPPORTED, "IterativeInitializationCollisionModel has no force (iterative_initialization.jl:1-12)");
     free_force(c);
     c->force_mode = 1; c->fx = fx; c->fy = fy;
     return 0;
@@ -962,8 +1033,20 @@ int lbm_set_force_field(lbm_ctx *c, const double *F) {
     if (!c || !F) return fail(LBM_ERR_INVALID, "null argument");
     CU(cudaSetDevice(c->desc.device));
     if (c->desc.collision == LBM_MRT && c->desc.ntau < 2) return fail(LBM_ERR_INVALID, "MRT forcing needs tau[1] (mrt.jl:94)");
+    if (c->desc.collision == LBM_ITERATIVE_INIT) return fail(LBM_ERR_UNSUPPORTED, "IterativeInitializationCollisionModel has no force (iterative_initialization.jl:1-12)");
     free_force(c);
     int rc = upload_as_elt(c, F, (size_t)2 * c->nyl * c->desc.nx, &c->field);
+    if (rc) return rc;
+    c->force_mode = 2;
+    return 0;
+}
+
+int lbm_set_velocity_field(lbm_ctx *c, const double *u0) {
+    if (!c || !u0) return fail(LBM_ERR_INVALID, "null argument");
+    if (c->desc.collision != LBM_ITERATIVE_INIT) return fail(LBM_ERR_STATE, "lbm_set_velocity_field is for LBM_ITERATIVE_INIT contexts");
+    CU(cudaSetDevice(c->desc.device));
+    free_force(c);
+    int rc = upload_as_elt(c, u0, (size_t)2 * c->nyl * c->desc.nx, &c->field);
     if (rc) return rc;
     c->force_mode = 2;
     return 0;
@@ -973,6 +1056,7 @@ int lbm_set_force_separable(lbm_ctx *c, int64_t t0, int32_t nsteps, const double
     if (!c || !fx_of_y || !fy_of_x || nsteps < 1) return fail(LBM_ERR_INVALID, "bad argument");
     CU(cudaSetDevice(c->desc.device));
     if (c->desc.collision == LBM_MRT && c->desc.ntau < 2) return fail(LBM_ERR_INVALID, "MRT forcing needs tau[1] (mrt.jl:94)");
+    if (c->desc.collision == LBM_ITERATIVE_INIT) return fail(LBM_ERR_UNSUPPORTED, "IterativeInitializationCollisionModel has no force (iterative_initialization.jl:1-12)");
     free_force(c);
     int rc = upload_as_elt(c, fx_of_y, (size_t)nsteps * c->nyl, &c->sep_fx);
     if (rc) return rc;
@@ -984,6 +1068,8 @@ int lbm_set_force_separable(lbm_ctx *c, int64_t t0, int32_t nsteps, const double
 }
 
 static int check_force_window(lbm_ctx *c, int64_t t0, int64_t n) {
+    if (c->desc.collision == LBM_ITERATIVE_INIT && c->force_mode != 2)
+        return fail(LBM_ERR_STATE, "LBM_ITERATIVE_INIT needs the prescribed velocity: call lbm_set_velocity_field first");
     if (c->force_mode == 3 && (t0 < c->sep_t0 || t0 + n > c->sep_t0 + c->sep_n))
         return fail(LBM_ERR_STATE, "steps [%lld, %lld) outside the separable force table [%lld, %lld)", (long long)t0,
                     (long long)(t0 + n), c->sep_t0, c->sep_t0 + c->sep_n);
@@ -1123,7 +1209,9 @@ int lbm_halo_path(const lbm_ctx *c) { return !c || c->desc.world == 1 ? 0 : (c->
 
 int lbm_set_option(lbm_ctx *c, const char *key, int64_t value) {
     if (!c || !key) return fail(LBM_ERR_INVALID, "null argument");
+    drop_graphs(c);
     if (!strcmp(key, "variant")) c->opt_variant = (int)value;
+    else if (!strcmp(key, "graph")) c->opt_graph = (int)value;
     else if (!strcmp(key, "overlap")) c->opt_overlap = (int)value;
     else if (!strcmp(key, "p2p")) c->opt_p2p = (int)value;
     else return fail(LBM_ERR_INVALID, "unknown option '%s'", key);
@@ -1208,12 +1296,12 @@ int lbm_reduce_errors(lbm_ctx *c, double tau_visc, double u_max, const lbm_sep_f
 
 int lbm_reduce(lbm_ctx *c, int32_t kind, double *out, int32_t n) {
     if (!c || !out || n < 1) return fail(LBM_ERR_INVALID, "bad argument");
-    if (kind < LBM_REDUCE_MEAN_UX || kind > LBM_REDUCE_CONSERVED) return fail(LBM_ERR_INVALID, "reduce kind %d", kind);
+    if (kind < LBM_REDUCE_MEAN_UX || kind > LBM_REDUCE_DENSITY_CHANGE) return fail(LBM_ERR_INVALID, "reduce kind %d", kind);
     CU(cudaSetDevice(c->desc.device));
     int rc = wait_comm(c);
     if (rc) return rc;
     const size_t N = (size_t)c->nyl * c->desc.nx;
-    if (kind == LBM_REDUCE_VELOCITY_CHANGE && !c->u_old) {
+    if ((kind == LBM_REDUCE_VELOCITY_CHANGE || kind == LBM_REDUCE_DENSITY_CHANGE) && !c->u_old) {
         CU(cudaMalloc(&c->u_old, 2 * N * 8));
         CU(cudaMemsetAsync(c->u_old, 0, 2 * N * 8, c->stream));  // zeros(T, 2) per node, stopping_criteria.jl:64
     }

@@ -9,11 +9,12 @@ benchmarks and notebooks use); Julia's `f!` is spelled `f_`.  Arrays are Float64
 from . import _abi
 from ._abi import LbmError
 from .boundary_conditions import (BoundaryCondition, BounceBack, Direction, East, MovingWall, North, South, West)
-from .collision_models import MRT, SRT, TRT, CollisionModel, LatticeForce, TRT_Lambda
+from .collision_models import (MRT, SRT, TRT, CollisionModel, IterativeInitializationCollisionModel, LatticeForce,
+                               TRT_Lambda)
 from .initial_conditions import (AnalyticalEquilibrium, AnalyticalEquilibriumAndOffEquilibrium, AnalyticalVelocity,
                                  AnalyticalVelocityAndStress, ConstantDensity, InitializationStrategy,
-                                 IterativeInitializationMeiEtAl, ZeroVelocityInitialCondition, initialize,
-                                 initialize_on_device)
+                                 IterativeInitialization, IterativeInitializationMeiEtAl,
+                                 ZeroVelocityInitialCondition, initialize, initialize_mei_et_al, initialize_on_device)
 from .model import (DeviceState, LatticeBoltzmannModel, apply_, apply_boundary_conditions_, collide_,
                     collide_model_, next_model_, simulate, simulate_model, stream_, stream_model_)
 from .parallel import SlabComm, halo_rows_per_direction, slab_rows
@@ -21,8 +22,8 @@ from .problems import (CouetteFlow, DecayingShearFlow, FluidFlowProblem, LidDriv
                        LinearizedThermalDiffusion, LinearizedTransverseShearWave, PoiseuilleFlow, TGV,
                        TaylorGreenVortex, boundary_conditions, decay_time, delta_t, delta_x, has_external_force,
                        lattice_force, lattice_viscosity, viscosity)
-from .processing_methods import (CompareWithAnalyticalSolution, MeanVelocityStoppingCriteria, NoStoppingCriteria,
-                                 ProcessingMethod, StopCriteria, TakeSnapshots, TrackHydrodynamicErrors,
+from .processing_methods import (CompareWithAnalyticalSolution, DensityConvergence, MeanVelocityStoppingCriteria,
+                                 NoStoppingCriteria, ProcessIterativeInitialization, ProcessingMethod, StopCriteria, TakeSnapshots, TrackHydrodynamicErrors,
                                  VelocityConvergenceStoppingCriteria, process_)
 from .quadratures import (D2Q4, D2Q5, D2Q9, D2Q13, D2Q17, D2Q21, D2Q37, Quadrature, Quadratures, dimension, opposite,
                           order)

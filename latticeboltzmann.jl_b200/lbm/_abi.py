@@ -22,18 +22,19 @@ LBM_NCCL_ID_BYTES = 128
 # enums (include/lbm_b200.h)
 LATTICE_IDS = {"D2Q4": 0, "D2Q5": 1, "D2Q9": 2, "D2Q13": 3, "D2Q17": 4, "D2Q21": 5, "D2Q37": 6}
 F64, F32 = 0, 1
-SRT, TRT, MRT = 0, 1, 2
+SRT, TRT, MRT, ITERATIVE_INIT = 0, 1, 2, 3
 ARITH_EXACT, ARITH_FAST = 0, 1
 BC_BOUNCE_BACK, BC_MOVING_WALL = 0, 1
 NORTH, EAST, SOUTH, WEST = 0, 1, 2, 3
-REDUCE_MEAN_UX, REDUCE_VELOCITY_CHANGE, REDUCE_CONSERVED = 0, 1, 2
+REDUCE_MEAN_UX, REDUCE_VELOCITY_CHANGE, REDUCE_CONSERVED, REDUCE_DENSITY_CHANGE = 0, 1, 2, 3
 
 EXPORTS = [
     "lbm_abi_version", "lbm_last_error", "lbm_lattice_info", "lbm_nccl_unique_id", "lbm_create",
     "lbm_destroy", "lbm_local_rows", "lbm_upload_f", "lbm_upload_f_collision", "lbm_download_f",
     "lbm_upload_f_rows", "lbm_download_f_rows", "lbm_init_equilibrium_rows",
     "lbm_download_f_collision",
-    "lbm_set_force_none", "lbm_set_force_uniform", "lbm_set_force_field", "lbm_set_force_separable",
+    "lbm_set_force_none", "lbm_set_force_uniform", "lbm_set_force_field", "lbm_set_velocity_field",
+    "lbm_set_force_separable",
     "lbm_collide", "lbm_stream", "lbm_apply_bcs", "lbm_step", "lbm_sync", "lbm_moments", "lbm_reduce",
     "lbm_reduce_errors",
     "lbm_kernel_launches", "lbm_halo_path", "lbm_last_step_ms", "lbm_timer_start", "lbm_timer_stop", "lbm_set_option",
@@ -100,6 +101,7 @@ def lib():
     l.lbm_set_force_none.argtypes = [vp]
     l.lbm_set_force_uniform.argtypes = [vp, C.c_double, C.c_double]
     l.lbm_set_force_field.argtypes = [vp, vp]
+    l.lbm_set_velocity_field.argtypes = [vp, vp]
     l.lbm_set_force_separable.argtypes = [vp, C.c_int64, C.c_int32, vp, vp]
     l.lbm_collide.argtypes = [vp, C.c_int64, C.c_double]
     l.lbm_stream.argtypes = [vp]
@@ -266,6 +268,13 @@ class Context:
         F[:, :, 0] = _as_f64(Fx, (self.nx, self.ny_local))
         F[:, :, 1] = _as_f64(Fy, (self.nx, self.ny_local))
         check(lib().lbm_set_force_field(self._h, F.ctypes.data))
+
+    def set_velocity_field(self, ux, uy):
+        """ITERATIVE_INIT contexts: the lattice velocity (NX, NY_local) every node is held at."""
+        U = np.empty((self.nx, self.ny_local, 2), dtype=np.float64, order="F")
+        U[:, :, 0] = _as_f64(ux, (self.nx, self.ny_local))
+        U[:, :, 1] = _as_f64(uy, (self.nx, self.ny_local))
+        check(lib().lbm_set_velocity_field(self._h, U.ctypes.data))
 
     def set_force_separable(self, t0, fx_of_y, fy_of_x):
         """fx_of_y: (nsteps, NY_local), fy_of_x: (nsteps, NX), C order."""

@@ -56,6 +56,23 @@ class SRT(CollisionModelBase):
         return [self.tau]
 
 
+class IterativeInitializationCollisionModel(CollisionModelBase):
+    """IterativeInitializationCollisionModel(q, tau, problem) (collision_models/iterative_initialization.jl:1-41):
+    SRT towards an equilibrium whose velocity is pinned to `lattice_velocity(q, problem, x, y)`; only the density comes
+    from f.  The reference stores `nonlinear_term[x, y, i]`; here the device evaluates it from the velocity field."""
+
+    def __init__(self, q, tau, problem):
+        self.tau = float(tau)
+        self.q, self.problem = q, problem
+
+    def taus(self):
+        return [self.tau]
+
+    def velocity_field(self, y0=0, ny=None):
+        X, Y = self.problem.grid(y0, self.problem.NY if ny is None else ny)
+        return self.problem.lattice_velocity(self.q, X, Y)
+
+
 class TRT(CollisionModelBase):
     """TRT(tau_symmetric, tau_asymmetric, force) -- and the 2-argument convenience
     constructor TRT(tau_a, tau_s) with SWAPPED order (trt.jl:1-6)."""

@@ -39,10 +39,21 @@ class AnalyticalVelocity(InitializationStrategy):
 
 
 class IterativeInitializationMeiEtAl(InitializationStrategy):
-    """mei_et_al.jl -- out of scope."""
+    """IterativeInitializationMeiEtAl(tau, eps) (mei_et_al.jl:4-10; defaults 1.0, 1e-7).  Runs on the device:
+    f = w, then up to 10000 collide-stream steps with the constant-velocity operator
+    (IterativeInitializationCollisionModel) until DensityConvergence fires.  `whole_field=True` replaces the reference's
+    single-node criterion (see DensityConvergence) by the norm over all nodes; `check_every` > 1 evaluates the
+    criterion only every so many steps (the reference checks after every step)."""
 
-    def __init__(self, tau=1.0, eps=1e-7):
+    def __init__(self, tau=1.0, eps=1e-7, whole_field=False, check_every=1, max_steps=10000):
         self.tau, self.eps = tau, eps
+        self.whole_field, self.check_every, self.max_steps = whole_field, int(check_every), int(max_steps)
+        self.steps_taken = None
+
+
+def IterativeInitialization():
+    """mei_et_al.jl:9-10."""
+    return IterativeInitializationMeiEtAl(1.0, 1e-7)
 
 
 def default_strategy(problem):
@@ -108,7 +119,9 @@ def initialize(strategy, q, problem, cm=None, rows=None):
     elif isinstance(strategy, AnalyticalVelocity):
         raise NotImplementedError("AnalyticalVelocity is broken in the reference (analytical_velocity.jl:21,39)")
     elif isinstance(strategy, IterativeInitializationMeiEtAl):
-        raise NotImplementedError("Mei et al. initialisation is out of scope (SURVEY.md section 8f)")
+        if rows is not None and rows != (0, problem.NY):
+            raise ValueError("the iterative initialisation runs on the whole domain (use initialize_mei_et_al with a comm)")
+        return initialize_mei_et_al(strategy, q, problem)
     else:
         raise TypeError(f"unknown initialisation strategy {strategy!r}")
     return np.asfortranarray(f, dtype=np.float64)
@@ -136,3 +149,26 @@ def initialize_on_device(strategy, q, problem, ctx, chunk_nodes=1 << 24):
             T = problem.lattice_temperature(q, X, Y)
         ctx.init_equilibrium_rows(off, rho, ux, uy, T)
     return True
+
+
+def initialize_mei_et_al(strategy, q, problem, dtype="f64", arith="exact", comm=None, device=None, model_out=None):
+    """initialize(::IterativeInitializationMeiEtAl, q, problem) (mei_et_al.jl:11-40) on the device.  Returns the
+    local slab of f_stream; `strategy.steps_taken` records how many collide-stream steps ran."""
+    from .collision_models import IterativeInitializationCollisionModel
+    from .model import LatticeBoltzmannModel, simulate_model
+    from .processing_methods import ProcessIterativeInitialization
+
+    class _EveryK(ProcessIterativeInitialization):
+        def noop(self, t, k=strategy.check_every):
+            return k > 1 and (t - 1) % k != 0
+
+    cm = IterativeInitializationCollisionModel(q, strategy.tau, problem)
+    pm = _EveryK(strategy.eps, problem, None, strategy.whole_field)
+    model = LatticeBoltzmannModel(problem, q, collision_model=cm, initialization_strategy=ZeroVelocityInitialCondition(),
+                                  process_method=pm, dtype=dtype, arith=arith, comm=comm, device=device)
+    try:
+        simulate_model(model, range(1, strategy.max_steps + 1))
+        strategy.steps_taken = model.state.steps_done
+        return model.f_stream
+    finally:
+        model.close()

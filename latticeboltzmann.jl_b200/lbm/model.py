@@ -8,7 +8,7 @@ import numpy as np
 
 from . import _abi
 from .boundary_conditions import BounceBack, MovingWall
-from .collision_models import MRT, SRT, TRT, CollisionModel, LatticeForce
+from .collision_models import (MRT, SRT, TRT, CollisionModel, IterativeInitializationCollisionModel, LatticeForce)
 from .initial_conditions import default_strategy, initialize, initialize_on_device
 from .processing_methods import ProcessingMethod
 
@@ -24,6 +24,8 @@ def _cm_code(cm):
         return _abi.TRT
     if isinstance(cm, MRT):
         return _abi.MRT
+    if isinstance(cm, IterativeInitializationCollisionModel):
+        return _abi.ITERATIVE_INIT
     raise TypeError(f"not a collision model: {cm!r}")
 
 
@@ -48,6 +50,7 @@ class DeviceState:
         self.y0, self.ny_local, self.nx, self.ny = ctx.y0, ctx.ny_local, ctx.nx, ctx.ny
         self._force_window = None
         self._static_force_set = False
+        self.steps_done = 0
 
     # -- force -------------------------------------------------------------------------------
     def max_batch(self):
@@ -57,6 +60,11 @@ class DeviceState:
         return 1  # opaque host closure: re-evaluated every step
 
     def prepare_force(self, t0, n, dt):
+        if isinstance(self.cm, IterativeInitializationCollisionModel):
+            if not self._static_force_set:
+                self.ctx.set_velocity_field(*self.cm.velocity_field(self.y0, self.ny_local))
+                self._static_force_set = True
+            return
         f = self.cm.force
         if f is None:
             if not self._static_force_set:
@@ -114,6 +122,7 @@ class DeviceState:
             self.prepare_force(t0 + done, m, dt)
             self.ctx.step(t0 + done, m, dt)
             done += m
+        self.steps_done = getattr(self, "steps_done", 0) + n
 
     # -- diagnostics -------------------------------------------------------------------------
     def moments(self, tau_visc, fields):

@@ -70,6 +70,28 @@ class VelocityConvergenceStoppingCriteria(StopCriteriaBase):
         return False
 
 
+class DensityConvergence(StopCriteriaBase):
+    """stopping_criteria/density_convergence.jl:1-17.  Restated literally: the loop `for x_idx in nx, y_idx in ny` (:9)
+    visits only the node (NX, NY), so norm(rho - rho_old) is the density change of that single node (everything else
+    stays at its initial 0).  `whole_field=True` uses the norm over all nodes, which is what the code evidently
+    intended.  rho_old lives on the device (lbm_reduce kind LBM_REDUCE_DENSITY_CHANGE)."""
+
+    def __init__(self, eps, problem=None, whole_field=False):
+        self.eps = float(eps)
+        self.problem = problem
+        self.whole_field = whole_field
+        self._corner_old = 0.0
+
+    def should_stop_(self, q, state):
+        s = state.reduce(_abi.REDUCE_DENSITY_CHANGE)
+        if self.whole_field:
+            d = float(np.sqrt(np.float64(s[0])))
+        else:
+            d = abs(float(s[1]) - self._corner_old)
+            self._corner_old = float(s[1])
+        return d < self.eps or d > 100.0
+
+
 def StopCriteria(problem):
     """:8-15."""
     if isinstance(problem, PoiseuilleFlow):
@@ -255,6 +277,21 @@ class TakeSnapshots(ProcessingMethodBase):
         self.snapshots.append(state.download_f())
         self.timesteps.append(t)
         return False
+
+
+class ProcessIterativeInitialization(ProcessingMethodBase):
+    """processing_methods/process_iterative_initialization.jl:1-26: only the stop criterion runs (the inner
+    process method call is commented out in the reference, :18)."""
+
+    def __init__(self, eps, problem, process_method=None, whole_field=False):
+        self.stop_criteria = DensityConvergence(eps, problem, whole_field)
+        self.internal_process_method = process_method
+        self.n_steps = 100
+        self.calls = 0
+
+    def next_(self, q, state, t):
+        self.calls += 1
+        return should_stop_(self.stop_criteria, q, state)
 
 
 def ProcessingMethod(problem, should_process, n_steps, stop_criteria=None):

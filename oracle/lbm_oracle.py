@@ -287,6 +287,28 @@ class MRT:
         self.force = force
 
 
+class IterativeInitializationCollisionModel:
+    """collision_models/iterative_initialization.jl:1-41 -- SRT towards an equilibrium whose velocity is pinned to the
+    problem's lattice velocity; only the density is taken from f.  `nonlinear_term` is precomputed exactly as the
+    reference does (:21-35): w_i rho_0 (a_H_1 + a_H_2 / 2), rho_0 = 1."""
+    force = None
+
+    def __init__(self, q, tau, problem):
+        self.tau = float(tau)
+        X, Y = problem.grid()
+        vx, vy = problem.velocity(X, Y)
+        ux, uy = problem.u_max * vx, problem.u_max * vy  # lattice_velocity, problems.jl:99-100
+        u_squared = ux * ux + uy * uy
+        cs = q.css
+        self.u0 = (ux, uy)
+        self.nonlinear_term = []
+        for i in range(q.Q):
+            u_dot_xi = float(q.cx[i]) * ux + float(q.cy[i]) * uy
+            a_H_1 = cs * u_dot_xi
+            a_H_2 = (cs * cs) * (u_dot_xi * u_dot_xi) - cs * u_squared
+            self.nonlinear_term.append(q.w[i] * 1.0 * (a_H_1 + a_H_2 / 2))
+
+
 def _force_at(force, time, shape):
     if force is None:
         return None
@@ -298,6 +320,14 @@ def collide(cm, q, f_in, time=0.0):
     """collide!(cm, q, f_in, f_out; time) -> new array f_out."""
     f = [f_in[i] for i in range(q.Q)]
     rho = density(q, f)
+    if isinstance(cm, IterativeInitializationCollisionModel):
+        # iterative_initialization.jl:42-60
+        out = np.empty_like(f_in)
+        tau = cm.tau
+        for i in range(q.Q):
+            feq = q.w[i] * rho + cm.nonlinear_term[i]
+            out[i] = (1 - 1 / tau) * f[i] + (1 / tau) * feq
+        return out
     ux, uy = velocity(q, f, rho)
     F = _force_at(cm.force, time, rho.shape)
     out = np.empty_like(f_in)
@@ -1027,6 +1057,53 @@ class VelocityConvergenceStoppingCriteria:
         if np.isnan(converged):
             return True
         return False
+
+
+class DensityConvergence:
+    """stopping_criteria/density_convergence.jl:1-17, restated literally: the loop `for x_idx in nx, y_idx in ny` (:9)
+    iterates over the two integers themselves, i.e. visits only the node (NX, NY); every other entry of rho / rho_old
+    stays 0, so norm(rho - rho_old) is the density change of that one node.  `whole_field=True` gives the criterion
+    the code evidently intended (all nodes)."""
+
+    def __init__(self, eps, problem, whole_field=False):
+        self.eps = float(eps)
+        self.rho_old = np.zeros((problem.NY, problem.NX))
+        self.rho = np.zeros((problem.NY, problem.NX))
+        self.whole_field = whole_field
+
+    def should_stop(self, q, f):
+        rho_now = density(q, [f[i] for i in range(q.Q)])
+        if self.whole_field:
+            self.rho_old[...] = self.rho
+            self.rho[...] = rho_now
+        else:
+            self.rho_old[-1, -1] = self.rho[-1, -1]
+            self.rho[-1, -1] = rho_now[-1, -1]
+        d = float(np.sqrt(np.sum((self.rho - self.rho_old) ** 2)))
+        return d < self.eps or d > 100.0
+
+
+class ProcessIterativeInitialization:
+    """processing_methods/process_iterative_initialization.jl:1-26 (the inner process method is never called, :18)."""
+
+    def __init__(self, eps, problem, whole_field=False):
+        self.stop = DensityConvergence(eps, problem, whole_field)
+        self.calls = 0
+
+    def next(self, q, f, t):
+        self.calls += 1
+        return self.stop.should_stop(q, f)
+
+
+def initialize_mei_et_al(q, problem, tau=1.0, eps=1e-7, max_steps=10000, whole_field=False):
+    """initialize(::IterativeInitializationMeiEtAl, q, problem) (initial_conditions/mei_et_al.jl:11-40):
+    f = w everywhere, then simulate(model, 1:10000) with the constant-velocity collision operator until the density
+    criterion fires.  Returns (f_stream, number of collide-stream steps taken)."""
+    f = np.stack([q.w[i] * np.ones((problem.NY, problem.NX)) for i in range(q.Q)])
+    pm = ProcessIterativeInitialization(eps, problem, whole_field)
+    model = Model(f, q, IterativeInitializationCollisionModel(q, tau, problem), problem.boundary_conditions(), pm)
+    simulate_model(model, range(1, max_steps + 1))
+    return model.f_stream, min(pm.calls, max_steps)
 
 
 def stop_criteria(problem):

@@ -149,6 +149,126 @@ def test_fused_steps_match_oracle(oracle, name, model, bck, arith):
     assert rel_max(got2, f2) < TOL64
 
 
+@pytest.mark.parametrize("name,model,bck,dtype", [
+    ("D2Q9", "TRT", "poiseuille", _abi.F64), ("D2Q9", "SRT", "cavity", _abi.F32), ("D2Q37", "TRT", "couette", _abi.F64),
+    ("D2Q17", "MRT", "none", _abi.F64), ("D2Q13", "TRT", "partial", _abi.F32),
+])
+def test_graph_replay_equals_plain_launches(oracle, name, model, bck, dtype):
+    """lbm_step replays captured CUDA graphs of 16 fused steps when a batch is long enough; the result must be
+    bit-identical to plain launches (option graph = 0), to the oracle, and survive force / option changes."""
+    O = oracle
+    qo = O.L.BY_NAME[name]()
+    nx, ny, nsteps = 36, 14, 53
+    f0 = random_populations(qo, nx, ny, seed=3)
+    force = (2e-6, 1e-6)
+    cm, code, taus = _models(O, qo, force)[model]
+    ob, hb = _bcs_pair(O, bck, nx, ny)
+    outs = []
+    for graph in (1, 0):
+        with _ctx(name, code, taus, hb, nx, ny, _abi.ARITH_EXACT, dtype) as c:
+            c.set_option("graph", graph)
+            c.set_force_uniform(*force)
+            c.upload_f(to_host_layout(f0))
+            l0 = c.kernel_launches
+            c.step(0, nsteps)
+            assert c.kernel_launches - l0 == nsteps  # replayed launches are counted like plain ones
+            a = to_oracle_layout(c.download_f())
+            c.set_force_uniform(2 * force[0], force[1])  # invalidates the captured parameters
+            c.step(nsteps, 40)
+            b = to_oracle_layout(c.download_f())
+            outs.append((a, b))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    if dtype == _abi.F64:
+        f = f0
+        for _ in range(nsteps):
+            f, _ = O.step(cm, qo, ob, f)
+        if model != "MRT":
+            assert np.array_equal(outs[0][0], f)
+        assert rel_max(outs[0][0], f) < TOL64
+
+
+
+class _PinnedVelocity:
+    """Minimal problem for IterativeInitializationCollisionModel: a given lattice velocity field."""
+
+    def __init__(self, ux, uy):
+        self.NY, self.NX = ux.shape
+        self.u_max = 1.0
+        self._u = (ux, uy)
+
+    def grid(self):
+        return np.meshgrid(np.arange(self.NX, dtype=float), np.arange(self.NY, dtype=float))
+
+    def velocity(self, X, Y, t=0.0):
+        return self._u
+
+
+@pytest.mark.parametrize("name", LATTICES)
+@pytest.mark.parametrize("dtype", [_abi.F64, _abi.F32])
+def test_iterative_initialization_collision_matches_oracle(oracle, name, dtype):
+    """LBM_ITERATIVE_INIT == IterativeInitializationCollisionModel (iterative_initialization.jl:42-60): collide alone and
+    fused multi-step; Float64 exact mode bit-identical."""
+    O = oracle
+    qo = O.L.BY_NAME[name]()
+    nx, ny, nsteps = 19, 11, 21
+    rng = np.random.default_rng(8)
+    u0 = (0.03 * rng.uniform(-1, 1, (ny, nx)), 0.03 * rng.uniform(-1, 1, (ny, nx)))
+    cm = O.IterativeInitializationCollisionModel(qo, 0.9, _PinnedVelocity(*u0))
+    f0 = random_populations(qo, nx, ny, seed=4)
+    want_c = O.collide(cm, qo, f0)
+    f = f0
+    for _ in range(nsteps):
+        f, _ = O.step(cm, qo, [], f)
+    with _abi.Context(nx, ny, name, _abi.ITERATIVE_INIT, [0.9], dtype=dtype, arith=_abi.ARITH_EXACT) as c:
+        c.upload_f(to_host_layout(f0))
+        with pytest.raises(lbm.LbmError):
+            c.step(0, 1)  # no velocity field yet
+        with pytest.raises(lbm.LbmError):
+            c.set_force_uniform(1e-6, 0.0)  # the operator has no force
+        c.set_velocity_field(u0[0].T, u0[1].T)
+        c.collide()
+        got_c = to_oracle_layout(c.download_f_collision())
+        c.upload_f(to_host_layout(f0))
+        c.step(0, nsteps)
+        got = to_oracle_layout(c.download_f())
+    if dtype == _abi.F64:
+        assert np.array_equal(got_c, want_c) and np.array_equal(got, f)
+    else:
+        assert rel_max(got_c, want_c) < 1e-6 and rel_max(got, f) < 1e-5
+
+
+@pytest.mark.parametrize("name,problem_kind,whole_field", [
+    ("D2Q9", "tgv", False), ("D2Q9", "tgv", True), ("D2Q17", "tgv", False), ("D2Q9", "couette", False), ("D2Q37", "shear", True),
+])
+def test_mei_et_al_initialisation_matches_oracle(oracle, name, problem_kind, whole_field):
+    """initialize(IterativeInitializationMeiEtAl(tau, eps), q, problem) (mei_et_al.jl:11-40) through the host mirror on
+    the device: same number of iterations as the oracle's literal restatement and bit-identical populations."""
+    O = oracle
+    qo = O.L.BY_NAME[name]()
+    q = getattr(lbm.Quadratures, name)
+    if problem_kind == "tgv":
+        po, ph = O.TGV(qo, 0.8, 1), lbm.TGV(q, 0.8, 1)
+    elif problem_kind == "couette":
+        po, ph = O.CouetteFlow(1 / 6, 2), lbm.CouetteFlow(1 / 6, 2)
+    else:
+        po, ph = O.DecayingShearFlow(1 / 6, 2), lbm.DecayingShearFlow(1 / 6, 2)
+    want, n_want = O.initialize_mei_et_al(qo, po, tau=1.0, eps=1e-9, whole_field=whole_field)
+    strategy = lbm.IterativeInitializationMeiEtAl(1.0, 1e-9, whole_field=whole_field)
+    got = to_oracle_layout(lbm.initialize(strategy, q, ph))
+    assert 2 < n_want < 10000 and strategy.steps_taken == n_want
+    assert np.array_equal(got, want)
+    # the point of the scheme: momentum pinned to the prescribed velocity, density relaxed to a consistent pressure
+    fl = [got[i] for i in range(qo.Q)]
+    rho = O.density(qo, fl)
+    ux, uy = O.velocity(qo, fl, rho)
+    X, Y = po.grid()
+    vx, vy = po.velocity(X, Y)
+    if problem_kind != "couette":  # (walls: the bounce-back rows do not hold the prescribed momentum)
+        assert np.abs(rho * ux - po.u_max * vx).max() < 5e-3 * po.u_max
+    assert abs(rho.sum() - rho.size) < 1e-9
+
+
+
 @pytest.mark.parametrize("name", ["D2Q9", "D2Q17", "D2Q37"])
 def test_force_field_and_separable(oracle, name):
     O = oracle

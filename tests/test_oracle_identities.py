@@ -196,3 +196,32 @@ def test_couette_moving_wall_converges_to_linear_profile():
     h = O.hydrodynamic_fields(q, pr, m.f_stream)
     X, Y = pr.grid()
     assert np.allclose(h["ux"], Y, atol=2e-3)
+
+
+@pytest.mark.parametrize("name", ["D2Q9", "D2Q13", "D2Q37"])
+@pytest.mark.parametrize("whole_field", [False, True])
+def test_mei_et_al_iterative_initialisation(name, whole_field):
+    """initial_conditions/mei_et_al.jl:11-40 + collision_models/iterative_initialization.jl + density_convergence.jl:
+    the constant-velocity relaxation conserves mass, pins the momentum to the prescribed lattice velocity and stops long
+    before the 10000-step cap (reference test: test/initial_conditions.jl:215-246, all @test_broken there)."""
+    q = O.L.BY_NAME[name]()
+    pr = O.TGV(q, 0.8, 1)
+    f, n = O.initialize_mei_et_al(q, pr, tau=1.0, eps=1e-7, whole_field=whole_field)
+    assert 10 < n < 1000
+    fl = [f[i] for i in range(q.Q)]
+    rho = O.density(q, fl)
+    ux, uy = O.velocity(q, fl, rho)
+    X, Y = pr.grid()
+    vx, vy = pr.velocity(X, Y)
+    assert abs(rho.sum() - rho.size) < 1e-10
+    assert np.abs(rho * ux - pr.u_max * vx).max() < 5e-3 * pr.u_max
+    assert np.abs(rho * uy - pr.u_max * vy).max() < 5e-3 * pr.u_max
+    # the literal criterion looks at the node (NX, NY) only and therefore fires earlier than the whole-field norm
+    n_lit = O.initialize_mei_et_al(q, pr, eps=1e-7, whole_field=False)[1]
+    n_all = O.initialize_mei_et_al(q, pr, eps=1e-7, whole_field=True)[1]
+    assert n_lit <= n_all
+    # nonlinear term: sum_i = 0 (mass), first moment = rho_0 u_0 (momentum)
+    cm = O.IterativeInitializationCollisionModel(q, 1.0, pr)
+    assert np.abs(sum(cm.nonlinear_term)).max() < 1e-16
+    jx = sum(q.cx[i] * cm.nonlinear_term[i] for i in range(q.Q))
+    assert np.abs(jx - cm.u0[0]).max() < 1e-15
