@@ -255,7 +255,7 @@ def test_mei_et_al_initialisation_matches_oracle(oracle, name, problem_kind, who
     want, n_want = O.initialize_mei_et_al(qo, po, tau=1.0, eps=1e-9, whole_field=whole_field)
     strategy = lbm.IterativeInitializationMeiEtAl(1.0, 1e-9, whole_field=whole_field)
     got = to_oracle_layout(lbm.initialize(strategy, q, ph))
-    assert 2 < n_want < 10000 and strategy.steps_taken == n_want
+    assert 1 <= n_want < 10000 and strategy.steps_taken == n_want
     assert np.array_equal(got, want)
     # the point of the scheme: momentum pinned to the prescribed velocity, density relaxed to a consistent pressure
     fl = [got[i] for i in range(qo.Q)]
@@ -376,6 +376,34 @@ def test_config_c1_shear_wave_1000_steps(oracle):
     row, ref = model.processing_method.df[-1], pm.df[-1]
     for k in ("error_rho", "error_u", "error_p", "error_sxy", "mass", "momentum", "energy"):
         assert abs(row[k] - ref[k]) <= 1e-9 * abs(ref[k]) + 1e-300, (k, row[k], ref[k])
+    model.close()
+
+
+@pytest.mark.parametrize("name,every", [("D2Q9", 10), ("D2Q13", [1, 7, 33, 40])])
+def test_lid_driven_cavity_with_snapshots(oracle, name, every):
+    """LidDrivenCavityFlow (East/South/West bounce-back + MovingWall North, last writer wins at
+    the top corners, lid_driven_cavity.jl:61-66) driven through simulate(model, time) with TakeSnapshots
+    (take_snapshots.jl:12-29); every snapshot bit-identical to the oracle's."""
+    O = oracle
+    qo = O.L.BY_NAME[name]()
+    q = getattr(lbm.Quadratures, name)
+    po, ph = O.LidDrivenCavityFlow(1 / 6, 1), lbm.LidDrivenCavityFlow(1 / 6, 1)
+    pmo = O.TakeSnapshots(po, every)
+    mo = O.make_model(po, qo, "TRT", "ZeroVelocityInitialCondition", pmo)
+    O.simulate_model(mo, range(0, 41))
+    pm = lbm.TakeSnapshots(ph, every)
+    model = lbm.LatticeBoltzmannModel(ph, q, collision_model=lbm.TRT, initialization_strategy=lbm.ZeroVelocityInitialCondition(),
+                                      process_method=pm)
+    lbm.simulate(model, range(0, 41))
+    assert pm.timesteps == pmo.timesteps and len(pm.snapshots) == len(pmo.snapshots) >= 4
+    for a, b in zip(pm.snapshots, pmo.snapshots):
+        assert np.array_equal(to_oracle_layout(a), b)
+    assert np.array_equal(to_oracle_layout(model.f_stream), mo.f_stream)
+    # the lid drags the fluid: x-momentum appears under the moving wall
+    fl = [mo.f_stream[i] for i in range(qo.Q)]
+    rho = O.density(qo, fl)
+    ux, _ = O.velocity(qo, fl, rho)
+    assert ux[-1].mean() > 0
     model.close()
 
 
