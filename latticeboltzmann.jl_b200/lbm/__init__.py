@@ -16,7 +16,7 @@ from .initial_conditions import (AnalyticalEquilibrium, AnalyticalEquilibriumAnd
                                  IterativeInitialization, IterativeInitializationMeiEtAl,
                                  ZeroVelocityInitialCondition, initialize, initialize_mei_et_al, initialize_on_device)
 from .model import (DeviceState, LatticeBoltzmannModel, apply_, apply_boundary_conditions_, collide_,
-                    collide_model_, next_model_, simulate, simulate_model, stream_, stream_model_)
+                    collide_model_, next_model_, simulate, simulate_model, stream, stream_, stream_model_)
 from .parallel import SlabComm, halo_rows_per_direction, slab_rows
 from .problems import (CouetteFlow, DecayingShearFlow, FluidFlowProblem, LidDrivenCavityFlow,
                        LinearizedThermalDiffusion, LinearizedTransverseShearWave, PoiseuilleFlow, TGV,

@@ -314,6 +314,22 @@ def stream_(q, f=None, f_new=None, *, f_old=None, dtype="f64"):
     return out
 
 
+def stream(q, f, f_new=None, *, dtype="f64"):
+    """stream(q, f, f_new = copy(f)) -- the scatter ("push") variant (stream.jl:6-16, 44-61).  It wraps an index at most
+    once (`if next_x > lx ... elseif next_x < 1`), so it is only defined for grids at least as large as the widest
+    lattice velocity (smaller ones index out of bounds under the reference's `@inbounds`); there it is the same
+    permutation as the periodic pull and runs on the same kernel.  Returns f_new."""
+    f = np.asarray(f)
+    h = int(np.abs(q.abscissae).max())
+    if f.shape[0] < h or f.shape[1] < h:
+        raise ValueError(f"push streaming needs a grid of at least {h} x {h} nodes for {q.name} (single wrap, stream.jl:44-61)")
+    out = stream_(q, f, dtype=dtype)
+    if f_new is not None:
+        f_new[...] = out
+        return f_new
+    return out
+
+
 def apply_(bcs, q, f_new, f_old, *, time=0.0, dtype="f64"):
     """apply!(bcs, q, f_new, f_old; time) (boundary_conditions.jl:6-16): in place on f_new."""
     if not isinstance(bcs, (list, tuple)):

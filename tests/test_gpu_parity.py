@@ -450,6 +450,23 @@ def test_array_level_operators():
         assert np.allclose(feq, f_new)
 
 
+@pytest.mark.parametrize("name,shape", [("D2Q9", (5, 4)), ("D2Q9", (1, 1)), ("D2Q13", (2, 6)), ("D2Q37", (3, 3)), ("D2Q37", (9, 4))])
+def test_push_stream_variant(oracle, name, shape):
+    """stream(q, f, f_new) -- the scatter variant with single wrap (stream.jl:6-16, 44-61) -- equals the oracle's literal
+    restatement wherever the reference is defined (grid >= widest velocity); smaller grids are rejected."""
+    O = oracle
+    qo = O.L.BY_NAME[name]()
+    q = getattr(lbm.Quadratures, name)
+    nx, ny = shape
+    f = random_populations(qo, nx, ny, seed=2)
+    got = to_oracle_layout(lbm.stream(q, to_host_layout(f)))
+    assert np.array_equal(got, O.stream_push(qo, f))
+    h = int(np.abs(q.abscissae).max())
+    if h > 1:
+        with pytest.raises(ValueError):
+            lbm.stream(q, to_host_layout(random_populations(qo, h - 1, 4)))
+
+
 def test_trt_equals_srt_and_mrt_only_at_tau_1():
     """test/collision_models.jl:3-114."""
     q = lbm.D2Q9()

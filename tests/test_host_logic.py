@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 import lbm
+from lbm import _abi
 import oracle.lbm_oracle as O
 from conftest import to_oracle_layout
 
@@ -181,6 +182,33 @@ def test_processing_method_noop_matches_next_semantics():
     assert isinstance(lbm.ProcessingMethod(lbm.TGV(lbm.D2Q9(), 0.8, 1), False, 10), lbm.TrackHydrodynamicErrors)
     assert isinstance(lbm.StopCriteria(pr), lbm.MeanVelocityStoppingCriteria) and lbm.StopCriteria(pr).tolerance == 1e-12
     assert isinstance(lbm.StopCriteria(lbm.TGV(lbm.D2Q9(), 0.8, 1)), lbm.NoStoppingCriteria)
+
+
+def test_density_convergence_literal_and_whole_field():
+    """DensityConvergence (density_convergence.jl:6-17): the literal restatement watches node (NX, NY) only (first call
+    compares with the initial 0), the whole-field variant uses the norm over all nodes; both stop above 100."""
+
+    class St:
+        def __init__(self, seq):
+            self.seq = list(seq)
+
+        def reduce(self, kind):
+            assert kind == _abi.REDUCE_DENSITY_CHANGE
+            return np.array(self.seq.pop(0) + [0.0, 0.0])
+
+    sc = lbm.DensityConvergence(1e-3, None)
+    st = St([[4.0, 1.0], [4.0, 1.5], [4.0, 1.5004], [0.0, 300.0]])
+    assert [lbm.processing_methods.should_stop_(sc, None, st) for _ in range(4)] == [False, False, True, True]
+    sc = lbm.DensityConvergence(1e-3, None, whole_field=True)
+    st = St([[4.0, 1.0], [1e-8, 1.0], [1e6, 1.0]])
+    assert [lbm.processing_methods.should_stop_(sc, None, st) for _ in range(3)] == [False, True, True]
+    pm = lbm.ProcessIterativeInitialization(1e-3, lbm.TGV(lbm.D2Q9(), 0.8, 1))
+    assert pm.n_steps == 100 and not pm.noop(1) and isinstance(pm.stop_criteria, lbm.DensityConvergence)
+    s = lbm.IterativeInitialization()
+    assert (s.tau, s.eps, s.max_steps, s.check_every) == (1.0, 1e-7, 10000, 1)
+    cm = lbm.IterativeInitializationCollisionModel(lbm.D2Q9(), 0.9, lbm.TGV(lbm.D2Q9(), 0.8, 1))
+    ux, uy = cm.velocity_field(4, 3)
+    assert cm.taus() == [0.9] and cm.force is None and ux.shape == uy.shape == (16, 3)
 
 
 def test_slab_rows_partition():
