@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -72,7 +73,10 @@ struct NcclApi {
 };
 static NcclApi g_nccl;
 
+static std::mutex g_nccl_mutex;  // contexts of one process may be created from several host threads
+
 static int load_nccl() {
+    std::lock_guard<std::mutex> lock(g_nccl_mutex);
     if (g_nccl.handle) return 0;
     const char *names[] = {getenv("LBM_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
     void *h = nullptr;

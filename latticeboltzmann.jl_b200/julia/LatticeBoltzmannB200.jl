@@ -120,5 +120,40 @@ function simulate(m::B200Model, time)
     m
 end
 
+# initialize(::IterativeInitializationMeiEtAl, q, problem) (src/initial_conditions/mei_et_al.jl:11-40) on the device:
+# collision kind 3 = IterativeInitializationCollisionModel (src/collision_models/iterative_initialization.jl), the
+# prescribed lattice velocity goes in once, DensityConvergence (stopping_criteria/density_convergence.jl:6-17) reads the
+# density of node (NX, NY) -- the only node its loop visits -- from lbm_reduce kind 3 (out[2]).
+function initialize_mei_et_al(strategy, q, problem)
+    t = pad -> ntuple(i -> i == 1 ? Float64(strategy.τ) : 0.0, pad)
+    zero_bc = LbmBc(0, 0, 0, 0, 0, 0, (0.0, 0.0), 1.0, 1.0)
+    bcs = boundary_conditions(problem)
+    desc = Ref(LbmDesc(1, problem.NX, problem.NY, lattice_id(q), 0, 3, 0, 1, t(LBM_MAX_TAU), length(bcs),
+                       ntuple(i -> i <= length(bcs) ? to_bc(bcs[i]) : zero_bc, LBM_MAX_BCS), 0, 0, 1, ntuple(_ -> 0x00, 128)))
+    ctx = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:lbm_create, LIB), Cint, (Ref{LbmDesc}, Ref{Ptr{Cvoid}}), desc, ctx))
+    xs, ys = range(problem)
+    u0 = [lattice_velocity(q, problem, xs[x], ys[y])[d] for x in 1:problem.NX, y in 1:problem.NY, d in 1:2]
+    f = [q.weights[i] for x in 1:problem.NX, y in 1:problem.NY, i in 1:length(q.weights)]
+    out, ρ_old = zeros(4), 0.0
+    try
+        check(ccall((:lbm_upload_f, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), ctx[], f))
+        check(ccall((:lbm_set_velocity_field, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), ctx[], u0))
+        for step in 1:10000
+            check(ccall((:lbm_step, LIB), Cint, (Ptr{Cvoid}, Int64, Int64, Cdouble), ctx[], step, 1, 0.0))
+            check(ccall((:lbm_reduce, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Int32), ctx[], 3, out, 4))
+            δρ = abs(out[2] - ρ_old); ρ_old = out[2]
+            (δρ < strategy.ϵ || δρ > 100.0) && break
+        end
+        check(ccall((:lbm_download_f, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), ctx[], f))
+    finally
+        ccall((:lbm_destroy, LIB), Cvoid, (Ptr{Cvoid},), ctx[])
+    end
+    f
+end
+
+# 0 single GPU, 1 NCCL send/recv, 2 peer-memory stores issued by the boundary-row kernel
+halo_path(m::B200Model) = ccall((:lbm_halo_path, LIB), Cint, (Ptr{Cvoid},), m.ctx)
+
 export B200Model
 end # module

@@ -33,9 +33,11 @@ def _worker(rank, world, idq, out, lattice, model, nx, ny, nsteps, walls, dtype,
         if walls:
             bcs = [lbm.BounceBack(lbm.South(), (1, nx), (1, ny)).to_abi(),
                    lbm.MovingWall(lbm.North(), (1, nx), (1, ny), [0.01, 0.0]).to_abi()]
+        if p2p < 0 and rank == world - 1:
+            os.environ["LBM_P2P"] = "0"  # ONE rank cannot (here: will not) map its neighbours -> all must agree on NCCL
         c = _abi.Context(nx, ny, lattice, code, taus, bcs, dtype=dtype, device=rank, rank=rank, world=world, nccl_id=nid)
         c.set_option("overlap", overlap)
-        c.set_option("p2p", p2p)
+        c.set_option("p2p", 1 if p2p else 0)
         path = c.halo_path
         assert (c.y0, c.ny_local) == lbm.slab_rows(ny, rank, world)
         c.set_force_uniform(1e-6, 2e-6)
@@ -102,7 +104,7 @@ def _run_slabs(lattice, model, walls, overlap, p2p, world=2, nx=40, ny=37, nstep
         mass += red[0]
     assert np.isclose(mass, O.density(qo, [want[i] for i in range(qo.Q)]).sum(), rtol=1e-13)
     assert len(paths) == 1, f"ranks disagree on the halo path: {paths}"
-    if not p2p:
+    if p2p <= 0:
         assert paths == {1}
     return paths.pop()
 
@@ -138,3 +140,52 @@ def test_more_slabs(world, lattice, model, walls):
     if _gpus() < world:
         pytest.skip(f"needs {world} GPUs")
     _run_slabs(lattice, model, walls, 1, 1, world=world, nx=136, ny=16 * world + 5, nsteps=15)
+
+
+def test_ranks_agree_on_the_halo_path_when_one_cannot_map_its_neighbours():
+    """lbm_create takes the min over ranks of "mapped my neighbours": a single rank that opts out (LBM_P2P=0 in its
+    environment only) moves every rank to the NCCL path -- no mixed protocols, results unchanged."""
+    assert _run_slabs("D2Q9", "TRT", True, 1, -1) == 1
+
+
+def test_two_slabs_in_one_process():
+    """Both contexts in ONE process (two host threads, one per GPU -- what a single Julia process driving several GPUs
+    does): the neighbours' buffers are reached through plain peer access instead of cudaIpc; same bit-identical result."""
+    import threading
+    import oracle.lbm_oracle as O
+    import lbm
+    from lbm import _abi
+    lattice, nx, ny, nsteps, world = "D2Q13", 72, 41, 40, 2
+    qo = O.L.BY_NAME[lattice]()
+    rng = np.random.default_rng(5)
+    f = np.stack([qo.w[i] * (1 + 0.01 * rng.uniform(-1, 1, (ny, nx))) for i in range(qo.Q)])
+    force = (1e-6, 2e-6)
+    cm = O.TRT(0.8, 1.1, force)
+    want = f
+    for _ in range(nsteps):
+        want, _ = O.step(cm, qo, [], want)
+    nid = _abi.nccl_unique_id()
+    res, errs = {}, []
+
+    def work(rank):
+        try:
+            c = _abi.Context(nx, ny, lattice, _abi.TRT, [0.8, 1.1], [], device=rank, rank=rank, world=world, nccl_id=nid)
+            c.set_force_uniform(*force)
+            c.upload_f(np.asfortranarray(np.transpose(f[:, c.y0:c.y0 + c.ny_local], (2, 1, 0))))
+            c.step(0, 3)
+            c.step(3, nsteps - 3)
+            res[rank] = (c.y0, np.transpose(c.download_f(), (2, 1, 0)), c.halo_path)
+            c.close()
+        except Exception as e:  # pragma: no cover
+            errs.append(repr(e))
+
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=240)
+    assert not errs, errs
+    assert len(res) == world
+    for rank, (y0, got, path) in res.items():
+        assert path == 2, "peer access between the two GPUs of one process should be available on an NVSwitch box"
+        assert np.array_equal(got, want[:, y0:y0 + got.shape[1]]), f"rank {rank}"

@@ -2,7 +2,7 @@
 # N-GPU box (N = $1): slab parity at world 3..N, then the scaling points of C2 (weak) and C3 (strong) on the peer-memory path
 N=${1:-4}
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_multi.py -x -q -k "more_slabs" --durations=3 > gpurun_out/pytest_slabs_n$N.log 2>&1; echo "pytest more_slabs rc=$?"; tail -6 gpurun_out/pytest_slabs_n$N.log
+timeout 900 python -m pytest tests/test_gpu_multi.py -x -q -k "more_slabs or one_process or agree_on" --durations=3 > gpurun_out/pytest_slabs_n$N.log 2>&1; echo "pytest more_slabs rc=$?"; tail -6 gpurun_out/pytest_slabs_n$N.log
 run() { # name nproc args...
   name=$1; n=$2; shift 2
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n "$@" > gpurun_out/$name.json 2> gpurun_out/$name.err
