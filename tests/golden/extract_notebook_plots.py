@@ -116,8 +116,8 @@ def _ticks(p):
             i = j
         else:
             i += 1
-    yl = [l for l in labels if l[0] < x0]          # left of the plot area
-    xl = [l for l in labels if l[0] >= x0 and l[1] > y0 + h]  # below it
+    xl = [l for l in labels if l[1] > y0 + h + 40]                 # a text line below the plot area
+    yl = [l for l in labels if l[1] <= y0 + h + 40 and l[0] < x0]  # left of it (the lowest one may hang below the axis)
     p["xticks"] = [(g, l[2], l[3]) for g, l in zip(p["xgrid"], xl)] if len(xl) == len(p["xgrid"]) else None
     p["yticks"] = [(g, l[2], l[3]) for g, l in zip(p["ygrid"], yl)] if len(yl) == len(p["ygrid"]) else None
 
@@ -179,6 +179,73 @@ def shear_wave_d2q9():
                         for k, s in zip(["error_u", "error_p", "error_sxy"], lines)})
 
 
+def tgv_convergence():
+    """taylor_green_vortex.ipynb cell 5 (code: cells 3-5): TGV(q, tau, scale, 31 scale, 17 scale, sqrt(0.01) / scale) on D2Q9,
+    AnalyticalEquilibrium, ProcessingMethod(problem, false, t_end), simulate(model, 1:t_end), t_end =
+    round(Int, decay_time(problem)); scatter markers ordered tau = 3.0, 2.0, 1.0, 0.8, each at scale = 1, 2, 4."""
+    panels = parse_panels(cell_svg("taylor_green_vortex.ipynb", 5))
+    taus, scales = [3.0, 2.0, 1.0, 0.8], [1, 2, 4]
+    errors = {}
+    for name, p in zip(["error_u", "error_p", "error_sxy", "error_sxx"], panels):
+        pts = [s["points"][0] for s in calibrated_series(p) if s["kind"] == "circle"]
+        assert len(pts) == len(taus) * len(scales), (name, len(pts))
+        assert [round(x) for x, _ in pts] == [31 * sc for _ in taus for sc in scales]
+        errors[name] = [[pts[i * len(scales) + j][1] for j in range(len(scales))] for i in range(len(taus))]
+    return dict(source="examples/notebooks/taylor_green_vortex.ipynb cell 5 (SVG scatter markers)", taus=taus, scales=scales,
+                NX=[31 * sc for sc in scales], NY=[17 * sc for sc in scales], errors=errors)
+
+
+TGV_INIT_STRATEGIES = ["ConstantDensity", "AnalyticalVelocityAndStress", "AnalyticalEquilibrium",
+                       "AnalyticalEquilibriumAndOffEquilibrium", "IterativeInitializationMeiEtAl(0.8, 1e-10)",
+                       "IterativeInitializationMeiEtAl(1.0, 1e-10)"]
+
+
+def tgv_init_strategies():
+    """taylor_green_vortex.ipynb cell 9 (code: cells 7-9): TGV(D2Q9(), 0.8, 2, 96, 72, 0.03), one run per initialisation
+    strategy, ProcessingMethod(problem, true, t_end) -> one TrackHydrodynamicErrors row per next! call of
+    simulate(model, 1:t_end), t_end = 840: 841 rows.  Kept: rows 1-20, then every 20th, and the last."""
+    panels = parse_panels(cell_svg("taylor_green_vortex.ipynb", 9))
+    keep = sorted(set(list(range(0, 20)) + list(range(19, 841, 20)) + [840]))
+    errors = {}
+    for name, p in zip(["error_u", "error_p", "error_sxx", "error_sxy"], panels):
+        lines = [s for s in calibrated_series(p) if s["kind"] == "line"]
+        assert len(lines) == len(TGV_INIT_STRATEGIES) and all(len(s["points"]) == 841 for s in lines)
+        assert all(abs(x - (i + 1)) < 0.01 + 1e-3 * (i + 1) for s in lines for i, (x, _) in enumerate(s["points"]))
+        errors[name] = [[s["points"][i][1] for i in keep] for s in lines]
+    return dict(source="examples/notebooks/taylor_green_vortex.ipynb cell 9 (SVG polylines, 841 points each)",
+                strategies=TGV_INIT_STRATEGIES, rows=[i + 1 for i in keep], n_rows=841, errors=errors)
+
+
+def couette_convergence():
+    """couette.ipynb cell 7 (code: cell 6): CouetteFlow(1.0, u_0 / scale, nu, 1, 5 scale, (1.0, 1.0)), nu = tau / (2 css),
+    tau = 0.8, SRT, ZeroVelocityInitialCondition, t_end = 1, TrackHydrodynamicErrors(problem, false, n_steps,
+    VelocityConvergenceStoppingCriteria(1e-7, problem)); error_u per quadrature over scale = 1, 2, 4, 8 (plotted at
+    x = 8 scale), one panel per u_0.  (The stored figure has 4 scales; the code cell was later edited to 6.)"""
+    panels = parse_panels(cell_svg("couette.ipynb", 7))
+    us = [0.01, 0.015, 0.02, 0.03, 0.06, 0.12]
+    lattices = ["D2Q9", "D2Q13", "D2Q17", "D2Q21", "D2Q37"]
+    assert len(panels) == len(us)
+    out = {}
+    for u0, p in zip(us, panels):
+        lines = [s for s in calibrated_series(p) if s["kind"] == "line" and s["color"] != "#808080"]
+        assert len(lines) == len(lattices)
+        assert all([round(x) for x, _ in s["points"]] == [8, 16, 32, 64] for s in lines)
+        out[str(u0)] = {l: [y for _, y in s["points"]] for l, s in zip(lattices, lines)}
+    return dict(source="examples/notebooks/couette.ipynb cell 7 (SVG polylines)", tau=0.8, u_0=us, lattices=lattices,
+                scales=[1, 2, 4, 8], error_u=out)
+
+
+def poiseuille_tau_sweep():
+    """poiseuille.ipynb cell 9 (code: cells 6-9): error_u of the D2Q9 TRT(tau, tau, force) Poiseuille solve (the diagonal of
+    the trt_magic_parameter study, PoiseuilleFlow((tau - 0.5) / 3, 1), ZeroVelocityInitialCondition, t_end = 100,
+    VelocityConvergenceStoppingCriteria(1e-7)) for tau = 0.51, 0.52, ..., 10.0."""
+    (p,) = parse_panels(cell_svg("poiseuille.ipynb", 9))
+    (s,) = calibrated_series(p)
+    assert len(s["points"]) == 950 and all(abs(x - (0.51 + 0.01 * i)) < 2e-4 for i, (x, _) in enumerate(s["points"]))
+    return dict(source="examples/notebooks/poiseuille.ipynb cell 9 (SVG polyline, 950 points)",
+                tau=[round(0.51 + 0.01 * i, 2) for i in range(950)], error_u=[y for _, y in s["points"]])
+
+
 def main():
     if not os.path.isdir(REF):
         sys.exit("the reference notebooks are not available here; the committed JSON is the fixture")
@@ -187,7 +254,12 @@ def main():
                  "values carry ~1e-5 relative calibration error",
         shear_wave_convergence=shear_wave_convergence(),
         shear_wave_d2q9=shear_wave_d2q9(),
+        tgv_convergence=tgv_convergence(),
+        tgv_init_strategies=tgv_init_strategies(),
+        couette_convergence=couette_convergence(),
+        poiseuille_tau_sweep=poiseuille_tau_sweep(),
     )
+    fixtures = json.loads(json.dumps(fixtures), parse_float=lambda v: float("%.7g" % float(v)))  # 7 digits are plenty
     json.dump(fixtures, open(OUT, "w"), indent=1)
     print("wrote", OUT)
 

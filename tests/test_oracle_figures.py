@@ -1,0 +1,151 @@
+"""Pins the oracle to the numbers behind the FIGURES of the reference's notebooks.
+
+tests/golden/notebook_figures.json holds the data points of five figures, recovered from the SVG the notebooks store
+(tests/golden/extract_notebook_plots.py; ~1e-5 relative calibration error).  Unlike the printed TRT table they cover
+every lattice (D2Q4 ... D2Q37), the moving-wall boundary on the multi-speed lattices, all initialisation strategies
+including the Mei et al. iteration, the Taylor-Green problem and 841-step time series of all four error norms:
+
+  shear_wave.ipynb cell 12   static shear wave, SRT + force, 7 lattices x 4 resolutions x (u, p, sigma_xy)
+  taylor_green_vortex.ipynb cell 5   TGV decay, tau = 3, 2, 1, 0.8 x 3 resolutions x (u, p, sigma_xy, sigma_xx)
+  taylor_green_vortex.ipynb cell 9   TGV 96 x 72, six initialisation strategies, every step, four norms
+  couette.ipynb cell 7       Couette (moving wall + bounce-back), 5 multi-speed lattices x 4 resolutions x 6 wall speeds
+  poiseuille.ipynb cell 9    D2Q9 TRT(tau, tau) Poiseuille, tau = 0.51 ... 10.0 (950 solves)
+
+The CPU suite checks a subset sized for a couple of minutes of numpy; tests/test_gpu_figures.py runs all of it on the device.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle.lbm_oracle as O
+
+FIG = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "notebook_figures.json")))
+RTOL = 2e-4  # calibration of the SVG coordinates is good to ~5e-5
+
+
+def close(value, ref, rtol=RTOL):
+    return abs(value - ref) <= rtol * abs(ref)
+
+
+# ---- shear_wave.ipynb cell 12 ------------------------------------------------------------------
+def shear_wave_row(q, scale, tau=0.8):
+    """notebook_examples.jl:34-69"""
+    pr = O.DecayingShearFlow(tau / (2.0 * q.css), scale, static=True)
+    n_steps = round(1.0 / pr.delta_t())
+    pm = O.TrackHydrodynamicErrors(pr, False, n_steps, O.NoStoppingCriteria())
+    return O.simulate(pr, q, pm=pm, t_end=1.0).pm.df[-1]
+
+
+SHEAR_CASES = [(n, s) for n in ["D2Q4", "D2Q5", "D2Q9", "D2Q13", "D2Q17", "D2Q21", "D2Q37"] for s in (1, 2, 4)] + \
+              [("D2Q9", 8), ("D2Q13", 8)]
+
+
+@pytest.mark.parametrize("name,scale", SHEAR_CASES)
+def test_shear_wave_convergence_figure(name, scale):
+    ref = FIG["shear_wave_convergence"]
+    row = shear_wave_row(O.L.BY_NAME[name](), scale)
+    i = ref["scales"].index(scale)
+    for k in ("error_u", "error_p", "error_sxy"):
+        want = ref["errors"][k][name]
+        assert want["N"][i] == 8 * scale
+        assert close(row[k], want["value"][i]), (name, scale, k, row[k], want["value"][i])
+    if name == "D2Q9":  # the single-lattice figure of cell 10 carries the same numbers
+        for k, v in FIG["shear_wave_d2q9"]["errors"].items():
+            assert close(row[k], v["value"][i]), (k, row[k], v["value"][i])
+
+
+# ---- taylor_green_vortex.ipynb cell 5 ----------------------------------------------------------
+@pytest.mark.parametrize("tau,scale", [(3.0, 1), (3.0, 2), (3.0, 4), (2.0, 1), (2.0, 2), (2.0, 4), (1.0, 1), (1.0, 2), (0.8, 1), (0.8, 2)])
+def test_tgv_convergence_figure(tau, scale):
+    ref = FIG["tgv_convergence"]
+    q = O.L.D2Q9()
+    pr = O.TGV(q, tau, scale, 31 * scale, 17 * scale, np.sqrt(0.01) / scale)
+    t_end = round(pr.decay_time())
+    m = O.make_model(pr, q, "SRT", strategy="AnalyticalEquilibrium", pm=O.processing_method(pr, False, t_end))
+    O.simulate_model(m, range(1, t_end + 1))
+    row = m.pm.df[-1]
+    i, j = ref["taus"].index(tau), ref["scales"].index(scale)
+    for k in ("error_u", "error_p", "error_sxy", "error_sxx"):
+        assert close(row[k], ref["errors"][k][i][j]), (tau, scale, k, row[k], ref["errors"][k][i][j])
+
+
+# ---- taylor_green_vortex.ipynb cell 9 ----------------------------------------------------------
+def tgv_init_series(strategy_index):
+    """cells 7-9: TGV(D2Q9(), 0.8, 2, 96, 72, 0.03), SRT, ProcessingMethod(problem, true, t_end), simulate(model, 1:t_end)"""
+    q = O.L.D2Q9()
+    pr = O.TGV(q, 0.8, 2, 96, 72, 0.03)
+    t_end = round(pr.decay_time())
+    assert t_end == 840
+    pm = O.TrackHydrodynamicErrors(pr, True, t_end, O.NoStoppingCriteria())
+    name = FIG["tgv_init_strategies"]["strategies"][strategy_index]
+    if name.startswith("IterativeInitializationMeiEtAl"):
+        tau = float(name.split("(")[1].split(",")[0])
+        f0, n_iter = O.initialize_mei_et_al(q, pr, tau=tau, eps=1e-10)
+        assert 100 < n_iter < 10000
+        m = O.Model(f0, q, O.collision_model("SRT", q, pr), pr.boundary_conditions(), pm)
+    else:
+        m = O.make_model(pr, q, "SRT", strategy=name, pm=pm)
+    O.simulate_model(m, range(1, t_end + 1))
+    return m.pm.df
+
+
+@pytest.mark.parametrize("strategy_index", [1, 3, 5])
+def test_tgv_initialisation_strategies_figure(strategy_index):
+    """AnalyticalVelocityAndStress, AnalyticalEquilibriumAndOffEquilibrium and the Mei et al. iteration (tau = 1): every
+    kept row of the 841-row time series, all four norms.  The Mei et al. curve is only reproduced by the LITERAL
+    restatement of DensityConvergence (single node, density_convergence.jl:9); the whole-field norm is 1.6 % off."""
+    ref = FIG["tgv_init_strategies"]
+    df = tgv_init_series(strategy_index)
+    assert len(df) == ref["n_rows"]
+    for k in ("error_u", "error_p", "error_sxx", "error_sxy"):
+        got = np.array([df[r - 1][k] for r in ref["rows"]])
+        want = np.array(ref["errors"][k][strategy_index])
+        rel = np.abs(got - want) / np.abs(want)
+        assert rel.max() < RTOL, (ref["strategies"][strategy_index], k, rel.max(), ref["rows"][int(rel.argmax())])
+
+
+def test_mei_et_al_whole_field_variant_is_not_what_the_reference_computes():
+    ref = FIG["tgv_init_strategies"]
+    q = O.L.D2Q9()
+    pr = O.TGV(q, 0.8, 2, 96, 72, 0.03)
+    f_lit, n_lit = O.initialize_mei_et_al(q, pr, tau=1.0, eps=1e-10)
+    f_all, n_all = O.initialize_mei_et_al(q, pr, tau=1.0, eps=1e-10, whole_field=True)
+    assert n_lit < n_all
+    pm = O.TrackHydrodynamicErrors(pr, True, 840, O.NoStoppingCriteria())
+    row = lambda f: (pm.df.clear(), pm.next(q, f, 1), pm.df[-1])[2]  # noqa: E731
+    # the state handed to the first step differs measurably in its pressure error
+    e_lit, e_all = row(f_lit)["error_p"], row(f_all)["error_p"]
+    assert abs(e_lit - e_all) > 1e-3 * e_lit
+
+
+# ---- couette.ipynb cell 7 ----------------------------------------------------------------------
+def couette_row(q, u0, scale, tau=0.8):
+    """cell 6: couette_convergence_analysis"""
+    pr = O.CouetteFlow(tau / (2.0 * q.css), NX=1, NY=5 * scale, domain_size=(1.0, 1.0), u_max=u0 / scale, convenience=False)
+    n_steps = round(1.0 / pr.delta_t())
+    pm = O.TrackHydrodynamicErrors(pr, False, n_steps, O.VelocityConvergenceStoppingCriteria(1e-7, pr))
+    return O.simulate(pr, q, pm=pm, strategy="ZeroVelocityInitialCondition", t_end=1.0).pm.df[-1]
+
+
+COUETTE_CASES = [(n, u, s) for n in ["D2Q9", "D2Q13", "D2Q17", "D2Q21", "D2Q37"] for u in (0.01, 0.06, 0.12) for s in (1, 2)] + \
+                [("D2Q9", 0.03, 4), ("D2Q17", 0.06, 4)]
+
+
+@pytest.mark.parametrize("name,u0,scale", COUETTE_CASES)
+def test_couette_moving_wall_figure(name, u0, scale):
+    ref = FIG["couette_convergence"]
+    row = couette_row(O.L.BY_NAME[name](), u0, scale)
+    want = ref["error_u"][str(u0)][name][ref["scales"].index(scale)]
+    # (errors of 1e-9 and below are differences of nearly equal numbers: a looser bar there)
+    assert close(row["error_u"], want, RTOL if want > 1e-8 else 2e-2), (name, u0, scale, row["error_u"], want)
+
+
+# ---- poiseuille.ipynb cell 9 -------------------------------------------------------------------
+@pytest.mark.parametrize("index", [0, 3, 17, 49, 120, 250, 400, 600, 800, 949])
+def test_poiseuille_tau_sweep_figure(index):
+    from test_oracle_golden import solve
+    ref = FIG["poiseuille_tau_sweep"]
+    tau = ref["tau"][index]
+    assert close(solve(tau, tau)["error_u"], ref["error_u"][index]), (tau,)
