@@ -1,0 +1,51 @@
+"""The host mirror of the Julia API (latticeboltzmann.jl_b200/lbm: problems, initialisation strategies, force data, the
+batching `simulate`, processing methods, stop criteria, unit scaling) run END TO END on the CPU against the reference's
+notebook figures: the device context is replaced by an oracle-backed stand-in (tests/_oracle_context.py, test
+infrastructure), everything above the C ABI is the product code.  The same test bodies run on the real CUDA library in
+tests/test_gpu_figures.py; here a subset sized for the CPU suite."""
+import copy
+
+import pytest
+
+import test_gpu_figures as G
+from _oracle_context import emulated_backend
+
+
+@pytest.fixture
+def host(monkeypatch):
+    with emulated_backend(monkeypatch) as lbm:
+        yield lbm
+
+
+def _trim_scales(monkeypatch, key, n):
+    fig = copy.deepcopy(G.FIG)
+    fig[key]["scales"] = fig[key]["scales"][:n]
+    monkeypatch.setattr(G, "FIG", fig)
+
+
+@pytest.mark.parametrize("name", ["D2Q9", "D2Q17"])
+def test_shear_wave_convergence_through_the_host_mirror(host, monkeypatch, name):
+    _trim_scales(monkeypatch, "shear_wave_convergence", 3)
+    G.test_shear_wave_convergence_figure(name)
+
+
+def test_tgv_convergence_through_the_host_mirror(host):
+    G.test_tgv_convergence_figure(2.0)
+
+
+@pytest.mark.parametrize("index", [3, 5])
+def test_tgv_initialisation_strategies_through_the_host_mirror(host, index):
+    """index 5: IterativeInitializationMeiEtAl(1.0, 1e-10) -- lbm.initialize drives the LBM_ITERATIVE_INIT context and the
+    DensityConvergence reduce step by step, then the run proper starts from the downloaded populations."""
+    G.test_tgv_initialisation_strategies_figure(index)
+
+
+@pytest.mark.parametrize("name,u0", [("D2Q13", 0.12), ("D2Q37", 0.12), ("D2Q9", 0.03)])
+def test_couette_moving_wall_through_the_host_mirror(host, monkeypatch, name, u0):
+    _trim_scales(monkeypatch, "couette_convergence", 2 if name == "D2Q9" else 3)
+    G.test_couette_moving_wall_figure(name, u0)
+
+
+def test_poiseuille_tau_sweep_through_the_host_mirror(host, monkeypatch):
+    monkeypatch.setattr(G, "POISEUILLE_INDICES", [0, 5, 49, 149, 449, 949])
+    G.test_poiseuille_tau_sweep_figure()
