@@ -246,6 +246,28 @@ def poiseuille_tau_sweep():
                 tau=[round(0.51 + 0.01 * i, 2) for i in range(950)], error_u=[y for _, y in s["points"]])
 
 
+def _profile_circles(panel, n_snapshots, nx):
+    pts = [s["points"][0] for s in calibrated_series(panel) if s["kind"] == "circle"]
+    assert len(pts) == n_snapshots * nx, len(pts)
+    return [[y for _, y in pts[k * nx:(k + 1) * nx]] for k in range(n_snapshots)], [x for x, _ in pts[:nx]]
+
+
+def shear_wave_snapshots():
+    """shear_wave.ipynb cells 3-4 and 6-7 (plot_snapshots, notebook_examples.jl:71-240): dimensionless sigma_xx and sigma_xy
+    along x at y_pos = round(Int, NY / 2) for the TakeSnapshots snapshots of
+      decaying: DecayingShearFlow(1/6, 4, A = 3.0, static = false), AnalyticalEquilibrium, snapshots at steps
+                round.(Int, [0, 0.05, 0.15, 0.25] ./ dt) .+ 1   (a travelling, decaying wave; no force)
+      static:   DecayingShearFlow(1/6, 16, A = 0.5, static = true), ZeroVelocityInitialCondition, snapshots at steps
+                round.(Int, [0.01, 0.1, 1, 10] ./ (nu dt))       (spin-up under the TIME-DEPENDENT force)."""
+    out = {}
+    for key, cell, nx in (("decaying", 4, 32), ("static", 7, 128)):
+        panels = parse_panels(cell_svg("shear_wave.ipynb", cell))
+        sxx, x = _profile_circles(panels[2], 4, nx)
+        sxy, _ = _profile_circles(panels[3], 4, nx)
+        out[key] = dict(NX=nx, x=x, sigma_xx=sxx, sigma_xy=sxy)
+    return dict(source="examples/notebooks/shear_wave.ipynb cells 4 and 7 (SVG scatter markers)", **out)
+
+
 def main():
     if not os.path.isdir(REF):
         sys.exit("the reference notebooks are not available here; the committed JSON is the fixture")
@@ -258,6 +280,7 @@ def main():
         tgv_init_strategies=tgv_init_strategies(),
         couette_convergence=couette_convergence(),
         poiseuille_tau_sweep=poiseuille_tau_sweep(),
+        shear_wave_snapshots=shear_wave_snapshots(),
     )
     fixtures = json.loads(json.dumps(fixtures), parse_float=lambda v: float("%.7g" % float(v)))  # 7 digits are plenty
     json.dump(fixtures, open(OUT, "w"), indent=1)

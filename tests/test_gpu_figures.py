@@ -17,6 +17,7 @@ FIG = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "notebook
 RTOL = 2e-4  # the SVG coordinates are good to ~5e-5
 LATTICES = ["D2Q4", "D2Q5", "D2Q9", "D2Q13", "D2Q17", "D2Q21", "D2Q37"]
 POISEUILLE_INDICES = list(range(0, 950, 10)) + [949]
+N_SNAPSHOTS = {"decaying": 4, "static": 4}
 
 
 def close(value, ref, rtol=RTOL):
@@ -123,3 +124,38 @@ def test_poiseuille_tau_sweep_figure():
         got = res.processing_method.df[-1]["error_u"]
         res.close()
         assert close(got, ref["error_u"][index]), (tau, got, ref["error_u"][index])
+
+
+@pytest.mark.parametrize("kind", ["decaying", "static"])
+def test_shear_wave_snapshot_profiles_figure(kind):
+    """shear_wave.ipynb cells 3-4 / 6-7: TakeSnapshots + plot_snapshots (notebook_examples.jl:71-240): dimensionless
+    sigma_xx and sigma_xy along x at y_pos = round(Int, NY / 2).  decaying = a travelling, decaying wave without force;
+    static = spin-up from rest under the time-dependent force (lbm_set_force_separable), 24 901 steps."""
+    ref = FIG["shear_wave_snapshots"][kind]
+    q = lbm.D2Q9()
+    if kind == "decaying":
+        problem = lbm.DecayingShearFlow(1 / 6, 4, static=False, A=3.0)
+        every = [round(s / problem.delta_t()) + 1 for s in (0.0, 0.05, 0.15, 0.25)]
+        strategy = lbm.AnalyticalEquilibrium()
+    else:
+        problem = lbm.DecayingShearFlow(1 / 6, 16, static=True, A=0.5)
+        nu = problem.viscosity()
+        every = [round(s / (nu * problem.delta_t())) for s in (0.01, 0.1, 1.0, 10.0)]
+        strategy = lbm.ZeroVelocityInitialCondition()
+    every = every[:N_SNAPSHOTS[kind]]
+    pm = lbm.TakeSnapshots(problem, every)
+    model = lbm.LatticeBoltzmannModel(problem, q, initialization_strategy=strategy, process_method=pm)
+    lbm.simulate(model, range(0, every[-1]))
+    model.close()
+    assert pm.timesteps[:len(every)] == every
+    tau = q.speed_of_sound_squared * problem.lattice_viscosity()
+    y_pos = round(problem.NY / 2) - 1
+    for a, b, name in ((0, 0, "sigma_xx"), (0, 1, "sigma_xy")):
+        scale = np.abs(np.array(ref[name])).max()  # the figure's resolution is a fraction of its axis range
+        for k in range(len(every)):
+            f = pm.snapshots[k]
+            rho = lbm.density(q, f)
+            u = lbm.velocity(q, f, rho)
+            sigma = problem.dimensionless_stress(lbm.deviatoric_tensor(q, tau, f, rho, u))
+            got = sigma[:, y_pos, a, b]
+            assert np.abs(got - np.array(ref[name][k])).max() < 5e-5 * scale, (kind, name, k)

@@ -49,3 +49,10 @@ def test_couette_moving_wall_through_the_host_mirror(host, monkeypatch, name, u0
 def test_poiseuille_tau_sweep_through_the_host_mirror(host, monkeypatch):
     monkeypatch.setattr(G, "POISEUILLE_INDICES", [0, 5, 49, 149, 449, 949])
     G.test_poiseuille_tau_sweep_figure()
+
+
+@pytest.mark.parametrize("kind", ["decaying", "static"])
+def test_shear_wave_snapshots_through_the_host_mirror(host, monkeypatch, kind):
+    """TakeSnapshots + the host-side moment functions; static: the separable time-dependent force tables"""
+    monkeypatch.setattr(G, "N_SNAPSHOTS", {"decaying": 4, "static": 3})
+    G.test_shear_wave_snapshot_profiles_figure(kind)

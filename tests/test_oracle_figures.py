@@ -10,6 +10,8 @@ including the Mei et al. iteration, the Taylor-Green problem and 841-step time s
   taylor_green_vortex.ipynb cell 9   TGV 96 x 72, six initialisation strategies, every step, four norms
   couette.ipynb cell 7       Couette (moving wall + bounce-back), 5 multi-speed lattices x 4 resolutions x 6 wall speeds
   poiseuille.ipynb cell 9    D2Q9 TRT(tau, tau) Poiseuille, tau = 0.51 ... 10.0 (950 solves)
+  shear_wave.ipynb cells 4, 7  sigma_xx / sigma_xy profiles of TakeSnapshots snapshots: a travelling decaying wave, and
+                             the spin-up of the static wave under its TIME-DEPENDENT force
 
 The CPU suite checks a subset sized for a couple of minutes of numpy; tests/test_gpu_figures.py runs all of it on the device.
 """
@@ -149,3 +151,36 @@ def test_poiseuille_tau_sweep_figure(index):
     ref = FIG["poiseuille_tau_sweep"]
     tau = ref["tau"][index]
     assert close(solve(tau, tau)["error_u"], ref["error_u"][index]), (tau,)
+
+
+# ---- shear_wave.ipynb cells 4 and 7 ------------------------------------------------------------
+def snapshot_case(kind):
+    q = O.L.D2Q9()
+    if kind == "decaying":  # cell 3
+        pr = O.DecayingShearFlow(1 / 6, 4, static=False, A=3.0)
+        every = [round(s / pr.delta_t()) + 1 for s in (0.0, 0.05, 0.15, 0.25)]
+        strategy = "AnalyticalEquilibrium"
+    else:                   # cell 6
+        pr = O.DecayingShearFlow(1 / 6, 16, static=True, A=0.5)
+        nu = pr.viscosity()
+        every = [round(s / (nu * pr.delta_t())) for s in (0.01, 0.1, 1.0, 10.0)]
+        strategy = "ZeroVelocityInitialCondition"
+    return q, pr, every, strategy
+
+
+@pytest.mark.parametrize("kind,n_snapshots", [("decaying", 4), ("static", 3)])
+def test_shear_wave_snapshot_profiles_figure(kind, n_snapshots):
+    """(static: the 4th snapshot is 24 901 steps in; the CPU suite stops after the third, the GPU suite runs all four)"""
+    ref = FIG["shear_wave_snapshots"][kind]
+    q, pr, every, strategy = snapshot_case(kind)
+    assert every == ([1, 52, 154, 256] if kind == "decaying" else [25, 249, 2490, 24901])
+    pm = O.TakeSnapshots(pr, every)
+    m = O.make_model(pr, q, "SRT", strategy=strategy, pm=pm)
+    O.simulate_model(m, range(0, every[n_snapshots - 1]))
+    assert pm.timesteps[:n_snapshots] == every[:n_snapshots]
+    y_pos = round(pr.NY / 2) - 1
+    for key, name in (("sxx", "sigma_xx"), ("sxy", "sigma_xy")):
+        scale = np.abs(np.array(ref[name])).max()  # the figure's resolution is a fraction of its axis range
+        for k in range(n_snapshots):
+            got = O.hydrodynamic_fields(q, pr, pm.snapshots[k])[key][y_pos]
+            assert np.abs(got - np.array(ref[name][k])).max() < 5e-5 * scale, (kind, name, k)
