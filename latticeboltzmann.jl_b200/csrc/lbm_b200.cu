@@ -149,7 +149,7 @@ struct lbm_ctx {
     long long sep_t0 = 0;
     int sep_n = 0;
     // diagnostics
-    double *partials = nullptr, *red_out = nullptr, *u_old = nullptr;
+    double *partials = nullptr, *red_out = nullptr, *u_old = nullptr, *rho_old = nullptr;
     int red_blocks = 2048;
     // multi-GPU
     ncclComm_t comm = nullptr;
@@ -678,7 +678,7 @@ void lbm_destroy(lbm_ctx *c) {
     p2p_unmap(c);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     if (c->arena) { cudaFree(c->arena); c->buf[0] = c->buf[1] = nullptr; }
-    for (void *p : {c->buf[0], c->buf[1], c->field, c->sep_fx, c->sep_fy, (void *)c->partials, (void *)c->red_out, (void *)c->u_old})
+    for (void *p : {c->buf[0], c->buf[1], c->field, c->sep_fx, c->sep_fy, (void *)c->partials, (void *)c->red_out, (void *)c->u_old, (void *)c->rho_old})
         if (p) cudaFree(p);
     for (cudaEvent_t e : {c->ev_b, c->ev_c, c->ev_t0, c->ev_t1, c->ev_u0, c->ev_u1, c->ev_fork})
         if (e) cudaEventDestroy(e);
@@ -1305,11 +1305,15 @@ int lbm_reduce(lbm_ctx *c, int32_t kind, double *out, int32_t n) {
     int rc = wait_comm(c);
     if (rc) return rc;
     const size_t N = (size_t)c->nyl * c->desc.nx;
-    if ((kind == LBM_REDUCE_VELOCITY_CHANGE || kind == LBM_REDUCE_DENSITY_CHANGE) && !c->u_old) {
+    if (kind == LBM_REDUCE_VELOCITY_CHANGE && !c->u_old) {
         CU(cudaMalloc(&c->u_old, 2 * N * 8));
         CU(cudaMemsetAsync(c->u_old, 0, 2 * N * 8, c->stream));  // zeros(T, 2) per node, stopping_criteria.jl:64
     }
-    ReduceArgs ra{kind, c->partials, c->u_old, c->red_out, c->red_blocks};
+    if (kind == LBM_REDUCE_DENSITY_CHANGE && !c->rho_old) {
+        CU(cudaMalloc(&c->rho_old, N * 8));
+        CU(cudaMemsetAsync(c->rho_old, 0, N * 8, c->stream));  // zeros(nx, ny), process_iterative_initialization.jl:9-10
+    }
+    ReduceArgs ra{kind, c->partials, kind == LBM_REDUCE_DENSITY_CHANGE ? c->rho_old : c->u_old, c->red_out, c->red_blocks};
     const bool pull = c->state == ST_COLLIDED;
     if (is64(c)) c->ops->reduce64(pull, make_params<double>(c, c->cur, c->cur), ra, c->stream);
     else c->ops->reduce32(pull, make_params<float>(c, c->cur, c->cur), ra, c->stream);
