@@ -111,6 +111,12 @@ class COracle:
         lib().oracle_apply_bcs(self._lat, self._nbc, self._bcs, nx, ny, f_new.ctypes, f_old.ctypes)
         return f_new
 
+    def steps_inplace(self, fs, fc, nsteps):
+        """Advance fs (f_stream, C-contiguous float64 [Q,NY,NX]) by nsteps in place; fc receives f_collision."""
+        Q, ny, nx = fs.shape
+        assert fs.flags.c_contiguous and fc.flags.c_contiguous and fs.dtype == np.float64 == fc.dtype and fc.shape == fs.shape
+        lib().oracle_steps(self._lat, C.byref(self._cm), self._nbc, self._bcs, nx, ny, fs.ctypes, fc.ctypes, int(nsteps))
+
     def steps(self, f_stream, nsteps):
         """Returns (f_stream, f_collision) after nsteps; inputs untouched."""
         fs = np.ascontiguousarray(f_stream, dtype=np.float64).copy()

@@ -321,3 +321,28 @@ def test_separable_expected_fields_reproduce_the_analytic_fields():
                         E = E + a * xv[:, None] * yv[None, :]
                     assert np.abs(E - ref[f]).max() <= 1e-13 * max(np.abs(ref[f]).max(), 1e-300), (type(pr).__name__, t, f)
     assert lbm.LidDrivenCavityFlow(1 / 6, 1).expected_separable(q, 0.0) is None
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference`: the CPU restatement timed alone -- one JSON line with impl/cpu_baseline/e2e keys; under
+    torchrun only rank 0 works and prints."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+           "--cpu-n", "128", "--cpu-steps", "20"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-1500:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "MLUPS" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert "128x128" in d["cpu_baseline"]["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0 and d["vs_baseline"] is None and "workload" in d["config"]
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
