@@ -7,13 +7,22 @@ THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only ``tests/``,
 library.
 
 Parity pin: the reference itself (Julia) cannot run in this image, so the
-oracle is pinned by (1) the only numeric golden table the reference ships,
+oracle is pinned by outputs the reference left in its repository:
+(1) the numeric golden table it prints,
 ``examples/notebooks/trt_magic_parameter.ipynb:109-176`` (committed under
-``tests/golden/trt_magic_parameter.json``; ``tests/test_oracle_golden.py``),
-and (2) every identity the reference's own tests assert (``test/*.jl``;
-``tests/test_oracle_identities.py``).  Lattices/models not covered by the golden
-table (D2Q13..37 full steps, MRT tau != 1, MovingWall values) are pinned by
-those identities only.
+``tests/golden/trt_magic_parameter.json``; ``tests/test_oracle_golden.py``);
+(2) the numbers behind its notebook FIGURES, recovered from the stored SVG to
+~1e-5 relative (``tests/golden/extract_notebook_plots.py`` ->
+``tests/golden/notebook_figures.json``; ``tests/test_oracle_figures.py``):
+shear-wave convergence on all 7 lattices, TGV convergence, 841-step error time
+series for six initialisation strategies incl. the Mei et al. iteration,
+Couette with MovingWall + BounceBack on D2Q9..D2Q37, the 950-point TRT(tau, tau)
+Poiseuille sweep, snapshot stress profiles under the time-dependent force;
+(3) every identity the reference's own tests assert (``test/*.jl``;
+``tests/test_oracle_identities.py``).
+Not covered by any reference number or figure (pinned by restatement and
+identities only): MRT with tau != 1, TRT with tau_s != tau_a on the multi-speed
+lattices.
 
 Array convention: Julia ``f[x, y, i]`` (column-major, 1-based) is stored here as
 ``f[i, y, x]`` (numpy C order, 0-based) -- the same bytes.  Every function
