@@ -20,8 +20,11 @@ from .model import (DeviceState, LatticeBoltzmannModel, apply_, apply_boundary_c
 from .parallel import SlabComm, halo_rows_per_direction, slab_rows
 from .problems import (CouetteFlow, DecayingShearFlow, FluidFlowProblem, LidDrivenCavityFlow,
                        LinearizedThermalDiffusion, LinearizedTransverseShearWave, PoiseuilleFlow, TGV,
-                       TaylorGreenVortex, boundary_conditions, decay_time, delta_t, delta_x, has_external_force,
-                       lattice_force, lattice_viscosity, viscosity)
+                       TaylorGreenVortex, boundary_conditions, decay, decay_time, delta_t, delta_x, dimensionless_density,
+                       dimensionless_force, dimensionless_pressure, dimensionless_stress, dimensionless_temperature,
+                       dimensionless_velocity, dimensionless_viscosity, force, has_external_force, lattice_density,
+                       lattice_force, lattice_pressure, lattice_temperature, lattice_velocity, lattice_viscosity, range_,
+                       viscosity)
 from .processing_methods import (CompareWithAnalyticalSolution, DensityConvergence, MeanVelocityStoppingCriteria,
                                  NoStoppingCriteria, ProcessIterativeInitialization, ProcessingMethod, StopCriteria, TakeSnapshots, TrackHydrodynamicErrors,
                                  VelocityConvergenceStoppingCriteria, process_)

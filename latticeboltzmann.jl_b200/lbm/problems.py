@@ -116,6 +116,69 @@ def has_external_force(p):
     return p.has_external_force()
 
 
+# Julia's generic functions over problems (problems.jl:97-119), as free functions with the reference's argument order
+def lattice_density(q, problem, x, y, t=0.0):
+    return problem.lattice_density(q, x, y, t)
+
+
+def lattice_velocity(q, problem, x, y, t=0.0):
+    return problem.lattice_velocity(q, x, y, t)
+
+
+def lattice_pressure(q, problem, x, y, t=0.0):
+    return problem.lattice_pressure(q, x, y, t)
+
+
+def lattice_temperature(q, problem, x, y, t=0.0):
+    return problem.lattice_temperature(q, x, y, t)
+
+
+def dimensionless_viscosity(problem):
+    return problem.nu * problem.delta_x() ** 2 / problem.delta_t()
+
+
+def dimensionless_density(problem, rho):
+    return rho
+
+
+def dimensionless_velocity(problem, u):
+    return u / problem.u_max
+
+
+def dimensionless_pressure(q, problem, p):
+    return p
+
+
+def dimensionless_temperature(q, problem, T):
+    return T
+
+
+def dimensionless_force(problem, F):
+    return F / (problem.u_max * problem.delta_t())
+
+
+def dimensionless_stress(problem, sigma):
+    return sigma * (1 / problem.u_max ** 2)
+
+
+def force(problem, x, y, t=0.0):
+    """force(problem, x, y, t): the problem's own method, [0, 0] for the unforced ones (problems.jl:62-75)."""
+    if hasattr(problem, "force"):
+        return problem.force(x, y, t)
+    z = 0.0 * (np.asarray(x, dtype=np.float64) + y)
+    return z, z
+
+
+def decay(problem, x, y, t):
+    """decay(problem, x, y, t) (decaying_shear_flow.jl:117-129, taylor_green_vortex.jl)."""
+    return problem.decay(x, y, t)
+
+
+def range_(problem):
+    """range(problem) -> (x_range, y_range), cell-centred (problems.jl:18-26)."""
+    return problem.range()
+
+
 def delta_t(p):
     return p.delta_t()
 
