@@ -4,6 +4,9 @@
 loop semantics (`collide!(time = t*dt)`, `stream!`, `apply!`, `next!(model, t + 1)`, trailing
 `next!`), but consecutive steps whose `next!` is a no-op are issued as one fused device batch.
 """
+import atexit
+import collections
+
 import numpy as np
 
 from . import _abi
@@ -270,13 +273,55 @@ def simulate(problem_or_model, q_or_time=None, *, process_method=None, should_pr
 # ---------------------------------------------------------------------------------------------
 # array-level operators (the generic functions the reference's tests and benchmarks call)
 # ---------------------------------------------------------------------------------------------
+# The reference's tests and benchmarks call collide!/stream!/apply! on plain arrays, often in a loop.  A device context
+# per call would cost more than the operator (allocation, streams, constant upload), so the scratch contexts of the most
+# recent (lattice, model, relaxation times, boundary conditions, shape, dtype) combinations are kept alive.
+_SCRATCH_CACHE = collections.OrderedDict()
+_SCRATCH_CACHE_SIZE = 8
+
+
+def _scratch_key(q, cm, bcs, nx, ny, dtype, arith):
+    if not isinstance(cm, (SRT, TRT, MRT)):
+        return None  # (operators tied to a problem instance are not shared)
+    bkey = tuple((type(b).__name__, type(b.direction).__name__, tuple(b.xs), tuple(b.ys),
+                  tuple(np.ravel(getattr(b, "u", ()))), getattr(b, "rho", None)) for b in bcs)
+    return (q.name, type(cm).__name__, tuple(cm.taus()), bkey, nx, ny, str(dtype), str(arith))
+
+
 def _scratch(q, cm, bcs, f, dtype="f64", arith="exact"):
     f = np.asfortranarray(f, dtype=np.float64)
     nx, ny, Q = f.shape
     if Q != q.Q:
         raise ValueError(f"{q.name} has {q.Q} populations, array has {Q}")
+    try:
+        key = _scratch_key(q, cm, bcs, nx, ny, dtype, arith)
+    except Exception:
+        key = None
+    if key is not None and key in _SCRATCH_CACHE:
+        _SCRATCH_CACHE.move_to_end(key)
+        return _SCRATCH_CACHE[key], f
     ctx = make_context(q, cm, bcs, nx, ny, dtype, arith)
+    if key is not None:
+        _SCRATCH_CACHE[key] = ctx
+        while len(_SCRATCH_CACHE) > _SCRATCH_CACHE_SIZE:
+            _, old = _SCRATCH_CACHE.popitem(last=False)
+            old.close()
     return ctx, f
+
+
+def _release(ctx):
+    """end of an array-level call: cached scratch contexts stay alive, the others are destroyed"""
+    if not any(c is ctx for c in _SCRATCH_CACHE.values()):
+        ctx.close()
+
+
+def clear_scratch_contexts():
+    while _SCRATCH_CACHE:
+        _, ctx = _SCRATCH_CACHE.popitem()
+        ctx.close()
+
+
+atexit.register(clear_scratch_contexts)
 
 
 def collide_(collision_model, q, f_in=None, f_out=None, *, time=0.0, f_old=None, f_new=None, dtype="f64",
@@ -293,7 +338,7 @@ def collide_(collision_model, q, f_in=None, f_out=None, *, time=0.0, f_old=None,
         ctx.collide(0, time)
         out = ctx.download_f_collision()
     finally:
-        ctx.close()
+        _release(ctx)
     if f_out is not None:
         f_out[...] = out
     return out
@@ -308,7 +353,7 @@ def stream_(q, f=None, f_new=None, *, f_old=None, dtype="f64"):
         ctx.stream()
         out = ctx.download_f()
     finally:
-        ctx.close()
+        _release(ctx)
     if f_new is not None:
         f_new[...] = out
     return out
@@ -341,6 +386,6 @@ def apply_(bcs, q, f_new, f_old, *, time=0.0, dtype="f64"):
         ctx.apply_bcs(time)
         out = ctx.download_f()
     finally:
-        ctx.close()
+        _release(ctx)
     f_new[...] = out
     return f_new

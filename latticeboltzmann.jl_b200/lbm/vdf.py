@@ -46,8 +46,16 @@ def hermite(n, xi, q=None):
     return H
 
 
+_HERMITE_TABLES = {}
+
+
 def _hermite_table(q, n):
-    return [hermite(n, (int(q.abscissae[0, i]), int(q.abscissae[1, i])), q) for i in range(q.Q)]
+    """hermite(Val{n}, c_i, q) for every population; constant per lattice, so built once (the reference recomputes it per
+    node per population inside pressure / deviatoric_tensor, moments.jl:27,90)."""
+    key = (q.name, float(q.speed_of_sound_squared), n)
+    if key not in _HERMITE_TABLES:
+        _HERMITE_TABLES[key] = [hermite(n, (int(q.abscissae[0, i]), int(q.abscissae[1, i])), q) for i in range(q.Q)]
+    return _HERMITE_TABLES[key]
 
 
 def density(q, f):

@@ -56,3 +56,40 @@ def test_shear_wave_snapshots_through_the_host_mirror(host, monkeypatch, kind):
     """TakeSnapshots + the host-side moment functions; static: the separable time-dependent force tables"""
     monkeypatch.setattr(G, "N_SNAPSHOTS", {"decaying": 4, "static": 3})
     G.test_shear_wave_snapshot_profiles_figure(kind)
+
+
+def test_array_level_operators_reuse_their_scratch_context(host, monkeypatch):
+    """collide!/stream!/apply! on plain arrays (the reference's tests and benchmarks call them in loops): one device context
+    per (lattice, model, relaxation times, BCs, shape, dtype), kept alive between calls; results as the oracle's."""
+    import numpy as np
+    import oracle.lbm_oracle as O
+    from conftest import random_populations, to_host_layout, to_oracle_layout
+    from lbm import model
+    model.clear_scratch_contexts()
+    made = []
+    inner = model.make_context
+    monkeypatch.setattr(model, "make_context", lambda *a, **k: (made.append(a[:2]), inner(*a, **k))[1])
+    q, qo = host.D2Q9(), O.L.D2Q9()
+    f = random_populations(qo, 12, 7, seed=1)
+    for _ in range(3):
+        out = host.collide_(host.TRT(0.8, 1.1, None), q, to_host_layout(f))  # 3-argument form: (tau_s, tau_a, force)
+    assert len(made) == 1
+    assert np.array_equal(to_oracle_layout(out), O.collide(O.TRT(0.8, 1.1), qo, f))
+    host.collide_(host.TRT(0.8, 1.2, None), q, to_host_layout(f))  # other relaxation times: another context
+    assert len(made) == 2
+    for _ in range(2):
+        s = host.stream_(q, to_host_layout(f))
+    assert len(made) == 3 and np.array_equal(to_oracle_layout(s), O.stream(qo, f))
+    bcs = [host.BounceBack(host.North(), (1, 12), (1, 7)), host.MovingWall(host.North(), (1, 12), (1, 7), [0.01, 0.0])]
+    ob = [O.BounceBack("N", (1, 12), (1, 7)), O.MovingWall("N", (1, 12), (1, 7), [0.01, 0.0])]
+    want = O.stream(qo, f)
+    O.apply_bcs(ob, qo, want, f)
+    for _ in range(2):
+        fn = to_host_layout(O.stream(qo, f))
+        host.apply_(bcs, q, fn, to_host_layout(f))
+    assert len(made) == 4 and np.array_equal(to_oracle_layout(fn), want)
+    for k in range(model._SCRATCH_CACHE_SIZE + 2):  # the cache is bounded
+        host.collide_(host.SRT(0.6 + 0.01 * k), q, to_host_layout(f))
+    assert len(model._SCRATCH_CACHE) == model._SCRATCH_CACHE_SIZE
+    model.clear_scratch_contexts()
+    assert not model._SCRATCH_CACHE
