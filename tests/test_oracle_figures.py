@@ -184,3 +184,17 @@ def test_shear_wave_snapshot_profiles_figure(kind, n_snapshots):
         for k in range(n_snapshots):
             got = O.hydrodynamic_fields(q, pr, pm.snapshots[k])[key][y_pos]
             assert np.abs(got - np.array(ref[name][k])).max() < 5e-5 * scale, (kind, name, k)
+
+
+# ---- provenance of the fixture -----------------------------------------------------------------
+@pytest.mark.skipif(not os.path.isdir("/root/reference/examples/notebooks"), reason="the reference checkout is only in the build container")
+def test_fixture_is_what_the_extraction_script_produces():
+    """notebook_figures.json is exactly what tests/golden/extract_notebook_plots.py reads out of the reference's notebooks."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import extract_notebook_plots as E
+    fresh = dict(shear_wave_convergence=E.shear_wave_convergence(), tgv_convergence=E.tgv_convergence(),
+                 couette_convergence=E.couette_convergence(), shear_wave_snapshots=E.shear_wave_snapshots())
+    fresh = json.loads(json.dumps(fresh), parse_float=lambda v: float("%.7g" % float(v)))
+    for key, value in fresh.items():
+        assert FIG[key] == value, key
