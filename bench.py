@@ -239,7 +239,6 @@ def run_b200(a):
     import torch
     import torch.distributed as dist
     import lbm
-    from lbm import _abi
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
