@@ -268,6 +268,21 @@ def shear_wave_snapshots():
     return dict(source="examples/notebooks/shear_wave.ipynb cells 4 and 7 (SVG scatter markers)", **out)
 
 
+def wall_snapshots():
+    """poiseuille.ipynb cells 3-4 and couette.ipynb cells 2-4 (plot_snapshots methods for PoiseuilleFlow / CouetteFlow,
+    notebook_examples.jl:227-540): dimensionless sigma_xx and sigma_xy along y at x_pos = max(round(Int, NX / 2), 1) of the
+    TakeSnapshots snapshots of the spin-up from rest, D2Q9, SRT:
+      poiseuille: PoiseuilleFlow(1/6, 4) (3 x 20), snapshots at steps round.(Int, [0.01, 0.05, 0.1, 1.0] ./ (nu dt))
+      couette:    CouetteFlow(1/6, 16) (1 x 80), snapshots at round.(Int, [0, 0.005, 0.01, 0.05, 0.1, 0.5, 1, 5] ./ (nu dt)) .+ 1"""
+    out = {}
+    for key, nbk, n_snap, ny in (("poiseuille", "poiseuille.ipynb", 4, 20), ("couette", "couette.ipynb", 8, 80)):
+        panels = parse_panels(cell_svg(nbk, 4))
+        sxx, y = _profile_circles(panels[2], n_snap, ny)
+        sxy, _ = _profile_circles(panels[3], n_snap, ny)
+        out[key] = dict(NY=ny, y=y, sigma_xx=sxx, sigma_xy=sxy)
+    return dict(source="examples/notebooks/poiseuille.ipynb cell 4, couette.ipynb cell 4 (SVG scatter markers)", **out)
+
+
 def main():
     if not os.path.isdir(REF):
         sys.exit("the reference notebooks are not available here; the committed JSON is the fixture")
@@ -281,6 +296,7 @@ def main():
         couette_convergence=couette_convergence(),
         poiseuille_tau_sweep=poiseuille_tau_sweep(),
         shear_wave_snapshots=shear_wave_snapshots(),
+        wall_snapshots=wall_snapshots(),
     )
     fixtures = json.loads(json.dumps(fixtures), parse_float=lambda v: float("%.7g" % float(v)))  # 7 digits are plenty
     json.dump(fixtures, open(OUT, "w"), indent=1)

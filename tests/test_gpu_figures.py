@@ -17,7 +17,7 @@ FIG = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "notebook
 RTOL = 2e-4  # the SVG coordinates are good to ~5e-5
 LATTICES = ["D2Q4", "D2Q5", "D2Q9", "D2Q13", "D2Q17", "D2Q21", "D2Q37"]
 POISEUILLE_INDICES = list(range(0, 950, 10)) + [949]
-N_SNAPSHOTS = {"decaying": 4, "static": 4}
+N_SNAPSHOTS = {"decaying": 4, "static": 4, "poiseuille": 4, "couette": 8}
 
 
 def close(value, ref, rtol=RTOL):
@@ -159,3 +159,33 @@ def test_shear_wave_snapshot_profiles_figure(kind):
             sigma = problem.dimensionless_stress(lbm.deviatoric_tensor(q, tau, f, rho, u))
             got = sigma[:, y_pos, a, b]
             assert np.abs(got - np.array(ref[name][k])).max() < 5e-5 * scale, (kind, name, k)
+
+
+@pytest.mark.parametrize("kind", ["poiseuille", "couette"])
+def test_wall_bounded_snapshot_profiles_figure(kind):
+    """poiseuille.ipynb cells 3-4 / couette.ipynb cells 2-4: spin-up from rest between walls (bounce-back N+S with a force;
+    moving wall N + bounce-back S), TakeSnapshots, sigma_xx and sigma_xy along y at x_pos = max(round(Int, NX / 2), 1);
+    the last Couette snapshot is 192 001 steps in."""
+    ref = FIG["wall_snapshots"][kind]
+    q = lbm.D2Q9()
+    if kind == "poiseuille":
+        problem, snap, plus = lbm.PoiseuilleFlow(1 / 6, 4), (0.01, 0.05, 0.1, 1.0), 0
+    else:
+        problem, snap, plus = lbm.CouetteFlow(1 / 6, 16), (0, 0.005, 0.01, 0.05, 0.1, 0.5, 1.0, 5.0), 1
+    nu = problem.viscosity()
+    every = [round(s / (nu * problem.delta_t())) + plus for s in snap][:N_SNAPSHOTS[kind]]
+    pm = lbm.TakeSnapshots(problem, every)
+    model = lbm.LatticeBoltzmannModel(problem, q, initialization_strategy=lbm.ZeroVelocityInitialCondition(), process_method=pm)
+    lbm.simulate(model, range(0, every[-1]))
+    model.close()
+    assert pm.timesteps[:len(every)] == every
+    tau = q.speed_of_sound_squared * problem.lattice_viscosity()
+    x_pos = max(round(problem.NX / 2), 1) - 1
+    for a, b, name in ((0, 0, "sigma_xx"), (0, 1, "sigma_xy")):
+        scale = np.abs(np.array(ref[name])).max()
+        for k in range(len(every)):
+            f = pm.snapshots[k]
+            rho = lbm.density(q, f)
+            u = lbm.velocity(q, f, rho)
+            sigma = problem.dimensionless_stress(lbm.deviatoric_tensor(q, tau, f, rho, u))
+            assert np.abs(sigma[x_pos, :, a, b] - np.array(ref[name][k])).max() < 5e-5 * scale, (kind, name, k)

@@ -93,3 +93,9 @@ def test_array_level_operators_reuse_their_scratch_context(host, monkeypatch):
     assert len(model._SCRATCH_CACHE) == model._SCRATCH_CACHE_SIZE
     model.clear_scratch_contexts()
     assert not model._SCRATCH_CACHE
+
+
+@pytest.mark.parametrize("kind,n", [("poiseuille", 4), ("couette", 4)])
+def test_wall_bounded_snapshots_through_the_host_mirror(host, monkeypatch, kind, n):
+    monkeypatch.setattr(G, "N_SNAPSHOTS", dict(G.N_SNAPSHOTS, **{kind: n}))
+    G.test_wall_bounded_snapshot_profiles_figure(kind)

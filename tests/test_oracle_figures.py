@@ -186,6 +186,36 @@ def test_shear_wave_snapshot_profiles_figure(kind, n_snapshots):
             assert np.abs(got - np.array(ref[name][k])).max() < 5e-5 * scale, (kind, name, k)
 
 
+# ---- poiseuille.ipynb cell 4, couette.ipynb cell 4 ---------------------------------------------
+def wall_case(kind):
+    if kind == "poiseuille":
+        pr, snap, plus = O.PoiseuilleFlow(1 / 6, 4), (0.01, 0.05, 0.1, 1.0), 0
+    else:
+        pr, snap, plus = O.CouetteFlow(1 / 6, 16), (0, 0.005, 0.01, 0.05, 0.1, 0.5, 1.0, 5.0), 1
+    nu = pr.viscosity()
+    return pr, [round(s / (nu * pr.delta_t())) + plus for s in snap]
+
+
+@pytest.mark.parametrize("kind,n_snapshots", [("poiseuille", 4), ("couette", 5)])
+def test_wall_bounded_snapshot_profiles_figure(kind, n_snapshots):
+    """Spin-up from rest between walls (bounce-back N+S with a force; moving wall N + bounce-back S): sigma_xx and sigma_xy
+    along y at the recorded snapshots.  (couette: snapshots 6-8 are 19 201 ... 192 001 steps in -- GPU suite only.)"""
+    ref = FIG["wall_snapshots"][kind]
+    q = O.L.D2Q9()
+    pr, every = wall_case(kind)
+    assert every == ([24, 120, 240, 2400] if kind == "poiseuille" else [1, 193, 385, 1921, 3841, 19201, 38401, 192001])
+    pm = O.TakeSnapshots(pr, every)
+    m = O.make_model(pr, q, "SRT", strategy="ZeroVelocityInitialCondition", pm=pm)
+    O.simulate_model(m, range(0, every[n_snapshots - 1]))
+    assert pm.timesteps[:n_snapshots] == every[:n_snapshots]
+    x_pos = max(round(pr.NX / 2), 1) - 1
+    for key, name in (("sxx", "sigma_xx"), ("sxy", "sigma_xy")):
+        scale = np.abs(np.array(ref[name])).max()
+        for k in range(n_snapshots):
+            got = O.hydrodynamic_fields(q, pr, pm.snapshots[k])[key][:, x_pos]
+            assert np.abs(got - np.array(ref[name][k])).max() < 5e-5 * scale, (kind, name, k)
+
+
 # ---- provenance of the fixture -----------------------------------------------------------------
 @pytest.mark.skipif(not os.path.isdir("/root/reference/examples/notebooks"), reason="the reference checkout is only in the build container")
 def test_fixture_is_what_the_extraction_script_produces():
@@ -194,7 +224,8 @@ def test_fixture_is_what_the_extraction_script_produces():
     sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
     import extract_notebook_plots as E
     fresh = dict(shear_wave_convergence=E.shear_wave_convergence(), tgv_convergence=E.tgv_convergence(),
-                 couette_convergence=E.couette_convergence(), shear_wave_snapshots=E.shear_wave_snapshots())
+                 couette_convergence=E.couette_convergence(), shear_wave_snapshots=E.shear_wave_snapshots(),
+                 wall_snapshots=E.wall_snapshots())
     fresh = json.loads(json.dumps(fresh), parse_float=lambda v: float("%.7g" % float(v)))
     for key, value in fresh.items():
         assert FIG[key] == value, key
