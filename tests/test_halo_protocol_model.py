@@ -18,9 +18,12 @@ import itertools
 import pytest
 
 
-def explore(n_ranks, n_epochs, wait_for=1, signal_before_push=False):
-    """DFS over all interleavings.  Returns None if the protocol is safe and live, else a description of the violation."""
+def explore(n_ranks, n_epochs, wait_for=1, signal_before_push=False, final_wait=True):
+    """DFS over all interleavings.  Returns None if the protocol is safe and live, else a description of the violation.
+    After its last step every rank runs the end-of-batch hook (k_p2p_wait_epoch: WAIT for the last epoch) and then an
+    operation outside the protocol that pulls from the ghost rows of the final state (lbm_download_f / lbm_moments)."""
     order = ("WAIT", "READ", "SIGNAL", "PUSH") if signal_before_push else ("WAIT", "READ", "PUSH", "SIGNAL")
+    tail = ("WAIT", "READ") if final_wait else ("READ",)  # pseudo-step n_epochs + 1: wait for epoch n_epochs, read its halos
     up = lambda r: (r + 1) % n_ranks        # noqa: E731
     down = lambda r: (r - 1) % n_ranks      # noqa: E731
     # state: per rank (epoch being produced, index of the next action), flags[r] = (from_down, from_up),
@@ -34,9 +37,10 @@ def explore(n_ranks, n_epochs, wait_for=1, signal_before_push=False):
         enabled = False
         for r in range(n_ranks):
             e, a = pcs[r]
-            if e > n_epochs:
+            if e > n_epochs + 1:
                 continue
-            act = order[a]
+            acts = order if e <= n_epochs else tail
+            act = acts[a]
             nflags, nghost = flags, ghost
             if act == "WAIT":
                 if flags[r][0] < e - wait_for or flags[r][1] < e - wait_for:
@@ -50,7 +54,7 @@ def explore(n_ranks, n_epochs, wait_for=1, signal_before_push=False):
                 for nb, side in ((up(r), 0), (down(r), 1)):  # my top rows -> up's bottom ghosts; my bottom rows -> down's top ghosts
                     ne, na = pcs[nb]
                     # the rows being overwritten held state e - 2; nb reads them in its B(e - 1)
-                    nb_done_reading = ne > e - 1 or (ne == e - 1 and na > order.index("READ"))
+                    nb_done_reading = ne > e - 1 or (ne == e - 1 and na > order.index("READ"))  # (e - 1 <= n_epochs here)
                     if e >= 2 and not nb_done_reading:
                         return f"rank {r} step {e}: overwrites ghost rows rank {nb} has not read yet (it is at step {ne}, action {na})"
                     g[nb][e % 2][side] = e
@@ -62,12 +66,12 @@ def explore(n_ranks, n_epochs, wait_for=1, signal_before_push=False):
                 nflags = tuple(tuple(x) for x in f)
             enabled = True
             npcs = list(pcs)
-            npcs[r] = (e, a + 1) if a + 1 < len(order) else (e + 1, 0)
+            npcs[r] = (e, a + 1) if a + 1 < len(acts) else (e + 1, 0)
             nxt = (tuple(npcs), nflags, nghost)
             if nxt not in seen:
                 seen.add(nxt)
                 stack.append(nxt)
-        if not enabled and any(e <= n_epochs for e, _ in pcs):
+        if not enabled and any(e <= n_epochs + 1 for e, _ in pcs):
             return f"deadlock at {pcs} with flags {flags}"
     return None
 
@@ -88,6 +92,13 @@ def test_checker_catches_a_wait_that_is_one_epoch_short(n_ranks):
 def test_checker_catches_signalling_before_the_push(n_ranks):
     """publishing the epoch before the rows have been stored lets the neighbour read stale ghost rows"""
     msg = explore(n_ranks, 3, signal_before_push=True)
+    assert msg is not None and "ghost rows hold" in msg, msg
+
+
+@pytest.mark.parametrize("n_ranks", [2, 3])
+def test_checker_catches_a_missing_end_of_batch_wait(n_ranks):
+    """without k_p2p_wait_epoch a download right after the batch can pull halos that have not landed yet"""
+    msg = explore(n_ranks, 2, final_wait=False)
     assert msg is not None and "ghost rows hold" in msg, msg
 
 
