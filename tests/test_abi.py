@@ -88,3 +88,29 @@ def test_product_path_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, fn)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f"{fn} imports oracle/"
                 assert "lbm_oracle" not in text, f"{fn} references the oracle"
+
+
+def test_julia_shim_matches_the_c_abi():
+    """The `ccall` shim (unexecuted here: no Julia in the image) is kept honest statically: its structs mirror lbm_bc / lbm_desc
+    field for field, and every symbol it calls is declared in include/lbm_b200.h with the same number of arguments."""
+    jl = open(os.path.join(ROOT, "latticeboltzmann.jl_b200", "julia", "LatticeBoltzmannB200.jl")).read()
+    jtypes = {"Int32": _abi.C.c_int32, "Float64": _abi.C.c_double, "NTuple{2, Float64}": _abi.C.c_double * 2,
+              "NTuple{LBM_MAX_TAU, Float64}": _abi.C.c_double * _abi.LBM_MAX_TAU, "NTuple{LBM_MAX_BCS, LbmBc}": _abi.lbm_bc * _abi.LBM_MAX_BCS,
+              "NTuple{128, UInt8}": _abi.C.c_uint8 * 128}
+    for jname, ctype in (("LbmBc", _abi.lbm_bc), ("LbmDesc", _abi.lbm_desc)):
+        body = re.search(rf"struct {jname}\b[^\n]*\n(.*?)\nend", jl, re.S).group(1)
+        fields = re.findall(r"(\w+)::((?:NTuple\{[^}]*\})|\w+)", body)
+        assert [f for f, _ in fields] == [f for f, _ in ctype._fields_], jname
+        for (fname, jt), (_, ct) in zip(fields, ctype._fields_):
+            assert _abi.C.sizeof(jtypes[jt]) == _abi.C.sizeof(ct), (jname, fname, jt)
+    header = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "lbm_b200.h")).read(), flags=re.S)
+    decl = {m.group(1): m.group(2) for m in re.finditer(r"\b(lbm_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, re.S)}
+    calls = re.findall(r"ccall\(\(:(lbm_\w+), LIB\),\s*\w+,\s*\(([^)]*)\)", jl)
+    assert len(calls) >= 15
+    for name, argtypes in calls:
+        assert name in decl, f"{name} is not declared in the header"
+        n_julia = len([a for a in argtypes.split(",") if a.strip()])
+        params = decl[name].strip()
+        n_c = 0 if params in ("", "void") else len(params.split(","))
+        assert n_julia == n_c, (name, argtypes, params)
+    assert re.search(r"LBM_MAX_TAU, LBM_MAX_BCS = (\d+), (\d+)", jl).groups() == (str(_abi.LBM_MAX_TAU), str(_abi.LBM_MAX_BCS))
