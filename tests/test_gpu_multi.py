@@ -9,7 +9,7 @@ import pytest
 pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
 
 
-def _worker(rank, world, idq, out, lattice, model, nx, ny, nsteps, walls, dtype, overlap, p2p=1, single_steps=False):
+def _worker(rank, world, idq, out, lattice, model, nx, ny, nsteps, walls, dtype, overlap, p2p=1, single_steps=False, arith=0):
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, root)
@@ -35,7 +35,7 @@ def _worker(rank, world, idq, out, lattice, model, nx, ny, nsteps, walls, dtype,
                    lbm.MovingWall(lbm.North(), (1, nx), (1, ny), [0.01, 0.0]).to_abi()]
         if p2p < 0 and rank == world - 1:
             os.environ["LBM_P2P"] = "0"  # ONE rank cannot (here: will not) map its neighbours -> all must agree on NCCL
-        c = _abi.Context(nx, ny, lattice, code, taus, bcs, dtype=dtype, device=rank, rank=rank, world=world, nccl_id=nid)
+        c = _abi.Context(nx, ny, lattice, code, taus, bcs, dtype=dtype, arith=arith, device=rank, rank=rank, world=world, nccl_id=nid)
         c.set_option("overlap", overlap)
         c.set_option("p2p", 1 if p2p else 0)
         path = c.halo_path

@@ -1,0 +1,53 @@
+"""Float32 contexts on y-slabs (the P2P instances of the scalar and of the packed two-nodes-per-thread kernel).  Kept in a
+file that sorts last: written after the round's GPU budget was spent, so its first run on hardware is the driver's."""
+import numpy as np
+import pytest
+
+from test_gpu_multi import _worker
+
+pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
+
+
+def _slabs(lattice, model, walls, p2p, arith, nx=64, ny=45, nsteps=40, world=2):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    idq, out = ctx.Queue(), ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, idq, out, lattice, model, nx, ny, nsteps, walls, 1, 1, p2p, False, arith))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    parts = {}
+    for rank, y0, got, got2, red, err, path in res:
+        assert err is None, err
+        assert path == (2 if p2p else 1)
+        parts[y0] = got
+    return np.concatenate([parts[k] for k in sorted(parts)], axis=1)
+
+
+@pytest.mark.parametrize("lattice,model,walls,arith", [
+    ("D2Q9", "TRT", False, 1),   # fast arithmetic: the packed two-nodes-per-thread kernel (Q <= 13) and its P2P instance
+    ("D2Q13", "SRT", True, 1),
+    ("D2Q9", "SRT", True, 0),    # exact arithmetic: the scalar Float32 kernel
+    ("D2Q37", "TRT", True, 1),   # wide lattice: scalar kernel in both modes
+    ("D2Q13", "MRT", False, 0),
+])
+def test_float32_slabs(lattice, model, walls, arith):
+    """Peer-memory and NCCL halo paths give bit-identical Float32 results, within 1e-5 of the Float64 oracle."""
+    import oracle.lbm_oracle as O
+    nx, ny, nsteps = 64, 45, 40
+    qo = O.L.BY_NAME[lattice]()
+    rng = np.random.default_rng(5)
+    f = np.stack([qo.w[i] * (1 + 0.01 * rng.uniform(-1, 1, (ny, nx))) for i in range(qo.Q)])
+    force = (1e-6, 2e-6)
+    cm = {"SRT": O.SRT(0.8, force), "TRT": O.TRT(0.8, 1.1, force), "MRT": O.MRT(qo, [0.8, 0.9, 1.1, 1.3], force)}[model]
+    bcs = [O.BounceBack("S", (1, nx), (1, ny)), O.MovingWall("N", (1, nx), (1, ny), [0.01, 0.0])] if walls else []
+    want = f
+    for _ in range(nsteps):
+        want, _ = O.step(cm, qo, bcs, want)
+    a = _slabs(lattice, model, walls, 1, arith)
+    b = _slabs(lattice, model, walls, 0, arith)
+    assert np.array_equal(a, b), "halo path changes the Float32 result"
+    assert np.abs(a - want).max() / np.abs(want).max() < 1e-5
