@@ -119,9 +119,17 @@ def test_two_slabs_equal_single_domain(lattice, model, walls, overlap, p2p):
     _run_slabs(lattice, model, walls, overlap, p2p)
 
 
+def _peer_access(a=0, b=1):
+    import torch
+    return torch.cuda.device_count() > max(a, b) and torch.cuda.can_device_access_peer(a, b) and torch.cuda.can_device_access_peer(b, a)
+
+
 def test_peer_memory_path_is_taken_on_nvlink_boxes():
-    """On the B200 boxes (NVSwitch, every GPU can map every peer) the default halo path must be peer memory."""
-    assert _run_slabs("D2Q9", "TRT", False, 1, 1) == 2
+    """Where the GPUs can map each other (the B200 boxes: NVSwitch) the default halo path must be peer memory."""
+    path = _run_slabs("D2Q9", "TRT", False, 1, 1)
+    if not _peer_access():
+        pytest.skip("GPUs 0 and 1 cannot access each other's memory on this box: NCCL path (checked above)")
+    assert path == 2
 
 
 @pytest.mark.parametrize("lattice,model,walls,nx,ny,nsteps,single_steps", [
@@ -187,5 +195,5 @@ def test_two_slabs_in_one_process():
     assert not errs, errs
     assert len(res) == world
     for rank, (y0, got, path) in res.items():
-        assert path == 2, "peer access between the two GPUs of one process should be available on an NVSwitch box"
+        assert path == (2 if _peer_access() else 1), "peer access is available on this box but the NCCL path was taken"
         assert np.array_equal(got, want[:, y0:y0 + got.shape[1]]), f"rank {rank}"
