@@ -31,10 +31,17 @@ class FluidFlowProblem:
 
     def range(self):
         # problems.jl:18-26; y_range's stop uses domain_size[1] (sic)
-        dx = self.domain_size[0] / self.NX
-        dy = self.domain_size[1] / self.NY
-        xr, self._xstep = _julia_range(dx / 2, self.domain_size[0] - dx / 2, self.NX)
-        yr, self._ystep = _julia_range(dy / 2, self.domain_size[0] - dy / 2, self.NY)
+        key = (self.NX, self.NY, tuple(self.domain_size))
+        memo = self.__dict__.get("_range_memo")
+        if memo is None or memo[0] != key:  # (the grid of a problem does not change; diagnostics ask for it every call)
+            dx = self.domain_size[0] / self.NX
+            dy = self.domain_size[1] / self.NY
+            xr, xstep = _julia_range(dx / 2, self.domain_size[0] - dx / 2, self.NX)
+            yr, ystep = _julia_range(dy / 2, self.domain_size[0] - dy / 2, self.NY)
+            xr.setflags(write=False)
+            yr.setflags(write=False)
+            memo = self.__dict__["_range_memo"] = (key, xr, yr, xstep, ystep)
+        _, xr, yr, self._xstep, self._ystep = memo
         return xr, yr
 
     def range_steps(self):
@@ -265,13 +272,17 @@ class TGV(FluidFlowProblem):
         return z, z
 
     def expected_separable(self, q, t, y0=0, ny=None):
-        xr, yr = self._xy(y0, ny)
         kx, ky, td = self._k()
-        X, Y = xr * self.NX, yr * self.NY
         cs, u0, nu = q.speed_of_sound_squared, self.u_0, self.nu
         D1, D2 = np.exp(-t / td), np.exp(-2 * t / td)
-        cx, sx, cy, sy = np.cos(kx * X), np.sin(kx * X), np.cos(ky * Y), np.sin(ky * Y)
-        c2x, c2y = np.cos(2 * kx * X), np.cos(2 * ky * Y)
+        key = (self.NX, self.NY, y0, ny)
+        memo = self.__dict__.get("_sep_memo")
+        if memo is None or memo[0] != key:  # the spatial factors do not depend on t
+            xr, yr = self._xy(y0, ny)
+            X, Y = xr * self.NX, yr * self.NY
+            memo = self.__dict__["_sep_memo"] = (key, np.cos(kx * X), np.sin(kx * X), np.cos(ky * Y), np.sin(ky * Y),
+                                                  np.cos(2 * kx * X), np.cos(2 * ky * Y))
+        _, cx, sx, cy, sy, c2x, c2y = memo
         K = cs * (u0 ** 2 / 4) * D2
         s = D1 * u0
         return [
