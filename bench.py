@@ -63,6 +63,7 @@ def parse():
     ap.add_argument("--graph", type=int, default=1, help="1 = replay CUDA graphs of 16 fused steps (default), 0 = plain launches")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the post-timing multi-slab parity check against the oracle")
     ap.add_argument("--cpu-n", type=int, default=4096, help="CPU arm grid (default: the full 4096 x 4096 workload grid)")
     ap.add_argument("--cpu-steps", type=int, default=40, help="lattice steps of the cpu_baseline sample (reference arm: a tenth per bench step)")
     return ap.parse_args()
@@ -71,12 +72,22 @@ def parse():
 # ---------------------------------------------------------------------------------------------
 # CPU side: the oracle's C restatement (bench.py may execute oracle/ only here)
 # ---------------------------------------------------------------------------------------------
+def host_cores():
+    """Cores this process may use.  torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm must not inherit
+    that (round-1 SCALE records at N >= 2 ran the reference arm on one core), so the thread count is set explicitly."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 class CpuArm:
     """The C restatement of the reference algorithm on the host cores: state prepared once, then timed in place."""
 
     def __init__(self, n, lattice="D2Q9", collision="TRT"):
         import oracle.lbm_oracle as O
-        from oracle.c_oracle import COracle, num_threads
+        from oracle.c_oracle import COracle, lib as oracle_lib, num_threads
+        oracle_lib().oracle_set_threads(host_cores())
         q = O.L.BY_NAME[lattice]()
         pr = O.TGV(q, 0.8, max(n // 16, 1), NX=n, NY=n)
         cm = O.collision_model(collision, q, pr)
@@ -102,6 +113,15 @@ def cpu_restatement_mlups(n, steps, lattice="D2Q9", collision="TRT"):
     return v, arm.threads, secs
 
 
+def config_keys(workload, preset, grid_per_gpu, world, inner, arith, dtype, nq=Q, scaling="weak"):
+    """The `config` object both arms print: same keys, same values for the same workload (the driver compares them)."""
+    nx, nyl = int(grid_per_gpu[0]), int(grid_per_gpu[1])
+    return {"workload": workload, "preset": preset, "grid_per_gpu": [nx, nyl],
+            "grid_global": [nx, nyl * world if scaling == "weak" else nyl], "lattice_steps_per_bench_step": int(inner),
+            "arith": arith, "parallelism": f"y-slabs x{world}",
+            "l2": "working set (2 x %.2f GB per GPU) >> 126 MB L2; no flush needed" % (nx * nyl * nq * BYTES[dtype] / 1e9)}
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -122,10 +142,12 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "MLUPS", "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": 1e3 * wall / max(a.steps, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{a.lattice} {a.collision} Taylor-Green vortex decay, periodic (BASELINE configs[1])",
-                   "grid": [n, n], "note": "Julia is not installed; CPU arm = C restatement of the reference algorithm "
-                                           "(oracle/lbm_oracle.c, -O2 -ffp-contract=off, OpenMP over rows)"},
-        "cpu_baseline": {"value": value, "unit": "MLUPS", "cores": threads, "kind": "port", "sample": sample},
+        "config": config_keys(f"{a.lattice} {a.collision} Taylor-Green vortex decay, periodic (BASELINE configs[1])", "C2",
+                              [a.nx, a.ny], a.gpus, a.inner, a.arith, "f64"),
+        "note": "Julia is not installed; CPU arm = C restatement of the reference algorithm (oracle/lbm_oracle.c, -O2 "
+                "-ffp-contract=off, OpenMP over rows); it steps a bounded sample of the config's workload: " + sample,
+        "cpu_baseline": {"value": value, "unit": "MLUPS", "cores": threads, "nproc": os.cpu_count(), "kind": "port",
+                         "sample": sample},
         "e2e": {"value": value, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -215,6 +237,59 @@ def build_case(a, world, lbm):
     cm = lbm.CollisionModel(lbm.TRT, q, problem)
     return dict(q=q, problem=problem, cm=cm, nx=nx, ny=ny, scaling="strong", init=lbm.ZeroVelocityInitialCondition(),
                 workload="D2Q37 TRT Couette, moving wall North + bounce-back South, 8192x8192 (BASELINE configs[3])")
+
+
+def parity_check(world, rank, local, comm, lbm, torch, dist):
+    """OUTSIDE the timed region: multi-GPU parity made visible in the bench record (the GPU test box has one GPU).
+    20 steps of D2Q9 TRT Taylor-Green on a 4096 x (128 N) domain split into N y-slabs, Float64 exact and Float32 fast,
+    on both halo paths (peer-memory stores / NCCL send-recv); the slabs are gathered on rank 0 and compared with the C
+    oracle (oracle/, the checker -- never on the measured path) stepping the same initial state."""
+    nx, ny, nsteps = 4096, 128 * world, 20
+    q = lbm.D2Q9()
+    problem = lbm.TGV(q, 0.8, nx // 16, nx, ny)
+    cm = lbm.CollisionModel(lbm.TRT, q, problem)
+    cases, want, f0_full = [], None, None
+    for dtype, arith in (("f64", "exact"), ("f32", "fast")):
+        for p2p in ((1, 0) if world > 1 else (1,)):
+            ctx = lbm.model.make_context(q, cm, problem.boundary_conditions(), nx, ny, dtype, arith, comm, local)
+            ctx.set_option("p2p", p2p)
+            st = lbm.DeviceState(ctx, q, cm, comm)
+            f0 = lbm.initialize(lbm.AnalyticalEquilibrium(), q, problem, rows=(ctx.y0, ctx.ny_local))
+            ctx.upload_f(f0)
+            st.step(0, nsteps, problem.delta_t())
+            got = ctx.download_f()
+            path = ctx.halo_path
+            ctx.close()
+            # gather [Q][nyl][nx] slabs on rank 0 (equal slabs: ny = 128 N)
+            def gather(a):
+                t = torch.from_numpy(np.ascontiguousarray(np.transpose(a, (2, 1, 0)))).cuda()
+                if world == 1:
+                    return t.cpu().numpy()
+                parts = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
+                dist.gather(t, parts, dst=0)
+                return np.concatenate([x.cpu().numpy() for x in parts], axis=1) if rank == 0 else None
+            got_full = gather(got)
+            if f0_full is None:
+                f0_full = gather(f0)
+            if rank == 0:
+                if want is None:
+                    import oracle.lbm_oracle as O
+                    from oracle.c_oracle import COracle, lib as oracle_lib
+                    oracle_lib().oracle_set_threads(host_cores())
+                    qo = O.L.D2Q9()
+                    po = O.TGV(qo, 0.8, nx // 16, NX=nx, NY=ny)
+                    want, _ = COracle(qo, O.collision_model("TRT", qo, po)).steps(f0_full, nsteps)
+                err = float(np.max(np.abs(got_full - want)) / np.max(np.abs(want)))
+                cases.append({"dtype": dtype, "arith": arith, "halo_path": path, "max_rel_err": err,
+                              "bit_identical": bool(np.array_equal(got_full, want)),
+                              "tolerance": 1e-12 if dtype == "f64" else 1e-5})
+    if rank != 0:
+        return None
+    ok = all(c["max_rel_err"] < c["tolerance"] and (c["bit_identical"] or c["dtype"] != "f64") for c in cases)
+    return {"grid": [nx, ny], "slabs": world, "steps": nsteps, "workload": "D2Q9 TRT Taylor-Green vortex vs the C oracle",
+            "halo_paths": {"0": "single GPU", "1": "NCCL send/recv", "2": "peer-memory stores"}, "cases": cases, "ok": ok,
+            "max_rel_err": max(c["max_rel_err"] for c in cases),
+            "bit_identical": all(c["bit_identical"] for c in cases if c["dtype"] == "f64")}
 
 
 def measured_peak():
@@ -350,16 +425,21 @@ def run_b200(a):
         cpu = {"value": v, "unit": "MLUPS", "cores": threads, "kind": "port",
                "sample": f"{a.cpu_n}x{a.cpu_n} grid, {a.cpu_steps} lattice steps ({secs:.1f} s), C restatement "
                          f"(oracle/lbm_oracle.c) with OpenMP over rows"}
+    ctx.close()
+    parity = None if a.no_parity else parity_check(world, rank, local, comm, lbm, torch, dist)
+    if scaling == "weak":
+        cfg = config_keys(case["workload"], a.config, [nx, ny // world], world, inner, a.arith, a.dtype, q.Q, "weak")
+    else:
+        cfg = config_keys(case["workload"], a.config, [nx, ny], world, inner, a.arith, a.dtype, q.Q, "strong")
+        cfg["grid_per_gpu"] = [nx, nyl]
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "MLUPS", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": a.dtype, "data": "synthetic",
-            "config": {"workload": case["workload"], "preset": a.config,
-                       "grid_per_gpu": [nx, nyl], "grid_global": [nx, ny], "lattice_steps_per_bench_step": inner,
-                       "arith": a.arith, "variant": a.variant, "cuda_graphs": bool(a.graph), "parallelism": f"y-slabs x{world}", "halo_exchange": halo_path,
-                       "l2": "working set (2 x %.2f GB per GPU) >> 126 MB L2; no flush needed" % (nx * nyl * q.Q * BYTES[a.dtype] / 1e9),
-                       "wall_ms_per_step": region_ms / a.steps},
+            "config": cfg,
+            "details": {"grid_local": [nx, nyl], "variant": a.variant, "cuda_graphs": bool(a.graph), "halo_exchange": halo_path,
+                        "wall_ms_per_step": region_ms / a.steps},
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": int(launches),
@@ -367,8 +447,8 @@ def run_b200(a):
                          "traffic": traffic, "peak_source": peak_src, "bytes_per_update": b_alg,
                          "kernel_ms": kern_ms, "kernel": "k_step<%s, %s, pull>" % (type(cm).__name__, a.dtype)},
             "cpu_baseline": cpu,
+            "parity_check": parity,
         }))
-    ctx.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

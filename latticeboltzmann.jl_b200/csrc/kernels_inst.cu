@@ -566,9 +566,13 @@ __device__ __forceinline__ void p2p_signal(const KParams<T> &p) {
         if (atomicAdd(p.flags + P2P_CTA_COUNT, 1ULL) == total - 1) {
             p.flags[P2P_CTA_COUNT] = 0;
             __threadfence_system();
-            const unsigned long long e = p2p_epoch(p);
-            st_release_sys(p.flag_at_up, e);
-            st_release_sys(p.flag_at_dn, e);
+            // a launch whose own wait gave up computed with stale ghost rows: do not publish, so the failure
+            // propagates (the neighbours time out too) instead of spreading wrong rows
+            if (*(volatile unsigned long long *)(p.flags + P2P_TIMEOUT) == 0ULL) {
+                const unsigned long long e = p2p_epoch(p);
+                st_release_sys(p.flag_at_up, e);
+                st_release_sys(p.flag_at_dn, e);
+            }
         }
     }
 }

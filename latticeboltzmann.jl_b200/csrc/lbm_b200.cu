@@ -162,6 +162,7 @@ struct lbm_ctx {
     int opt_p2p = 1;           // lbm_set_option("p2p", 0) falls back to NCCL send/recv (same on all ranks)
     unsigned long long epoch = 0, batch = 0;
     bool p2p_in_batch = false; // a P2P launch ran in the current lbm_step batch
+    unsigned long long p2p_failed = 0;  // sticky: a device-side wait of the protocol gave up (epoch/token it waited for)
     // CUDA graphs of GRAPH_STEPS fused steps (launch-bound small slabs): one per source buffer, rebuilt when
     // anything baked into the kernel parameters changes (force data, options)
     cudaGraphExec_t graph[2] = {nullptr, nullptr};
@@ -173,7 +174,19 @@ struct lbm_ctx {
     bool timed = false;
     int opt_variant = 0;
     int opt_overlap = 1;
+    // reusable device staging for the Float32 import/export conversions (grown on demand, freed by lbm_destroy)
+    double *stage = nullptr;
+    size_t stage_bytes = 0;
 };
+
+static int need_stage(lbm_ctx *c, size_t bytes) {
+    if (c->stage_bytes >= bytes) return 0;
+    if (c->stage) { cudaStreamSynchronize(c->stream); cudaFree(c->stage); c->stage = nullptr; c->stage_bytes = 0; }
+    cudaError_t e = cudaMalloc(&c->stage, bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(LBM_ERR_NOMEM, "cudaMalloc(%zu bytes of staging): %s", bytes, cudaGetErrorString(e)); }
+    c->stage_bytes = bytes;
+    return 0;
+}
 
 template <typename T>
 static T *origin(const lbm_ctx *c, int b) {
@@ -411,12 +424,19 @@ static int p2p_connect(lbm_ctx *c) {
 }
 
 // after a stream synchronisation: did a device-side wait of the protocol give up?
+// Called by every entry point that synchronises the stream and hands data back; the failure is sticky (lbm_step
+// refuses to continue from a state computed with stale ghost rows).
 static int p2p_check(lbm_ctx *c) {
-    if (!c->p2p_on || c->epoch == 0) return 0;
-    unsigned long long v = 0;
-    CU(cudaMemcpyAsync(&v, my_flags(c) + P2P_TIMEOUT, sizeof(v), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    if (v) return fail(LBM_ERR_STATE, "peer-memory halo exchange timed out waiting for a neighbour (epoch/token %llu)", v);
+    if (!c->p2p_on || (c->epoch == 0 && c->batch == 0)) return 0;
+    if (!c->p2p_failed) {
+        unsigned long long v = 0;
+        CU(cudaMemcpyAsync(&v, my_flags(c) + P2P_TIMEOUT, sizeof(v), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        c->p2p_failed = v;
+    }
+    if (c->p2p_failed)
+        return fail(LBM_ERR_STATE, "peer-memory halo exchange timed out waiting for a neighbour (epoch/token %llu); the "
+                                   "populations of this context are invalid", c->p2p_failed);
     return 0;
 }
 
@@ -678,7 +698,7 @@ void lbm_destroy(lbm_ctx *c) {
     p2p_unmap(c);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     if (c->arena) { cudaFree(c->arena); c->buf[0] = c->buf[1] = nullptr; }
-    for (void *p : {c->buf[0], c->buf[1], c->field, c->sep_fx, c->sep_fy, (void *)c->partials, (void *)c->red_out, (void *)c->u_old, (void *)c->rho_old})
+    for (void *p : {c->buf[0], c->buf[1], c->field, c->sep_fx, c->sep_fy, (void *)c->partials, (void *)c->red_out, (void *)c->u_old, (void *)c->rho_old, (void *)c->stage})
         if (p) cudaFree(p);
     for (cudaEvent_t e : {c->ev_b, c->ev_c, c->ev_t0, c->ev_t1, c->ev_u0, c->ev_u1, c->ev_fork})
         if (e) cudaEventDestroy(e);
@@ -826,8 +846,9 @@ static int upload_buffer(lbm_ctx *c, int b, const double *f, int y0 = 0, int ny 
             CU(cudaMemcpy2DAsync(o + (size_t)i * c->plane, c->pitch * 8, f + (size_t)i * ny * nx, (size_t)nx * 8,
                                  (size_t)nx * 8, ny, cudaMemcpyHostToDevice, c->stream));
     } else {
-        double *stage = nullptr;
-        CU(cudaMalloc(&stage, (size_t)ny * nx * 8));
+        int rc = need_stage(c, (size_t)ny * nx * 8);
+        if (rc) return rc;
+        double *stage = c->stage;
         KParams<float> p = make_params<float>(c, b, b);
         p.dst += (size_t)y0 * c->pitch;
         p.nyl = ny;
@@ -836,8 +857,6 @@ static int upload_buffer(lbm_ctx *c, int b, const double *f, int y0 = 0, int ny 
             c->ops->import32(p, stage, i, c->stream);
             c->launches += 1;
         }
-        CU(cudaStreamSynchronize(c->stream));
-        CU(cudaFree(stage));
     }
     CU(cudaStreamSynchronize(c->stream));
     return 0;
@@ -884,8 +903,9 @@ static int download_buffer(lbm_ctx *c, int b, double *f, int y0 = 0, int ny = -1
             CU(cudaMemcpy2DAsync(f + (size_t)i * ny * nx, (size_t)nx * 8, o + (size_t)i * c->plane, c->pitch * 8,
                                  (size_t)nx * 8, ny, cudaMemcpyDeviceToHost, c->stream));
     } else {
-        double *stage = nullptr;
-        CU(cudaMalloc(&stage, (size_t)ny * nx * 8));
+        int rc = need_stage(c, (size_t)ny * nx * 8);
+        if (rc) return rc;
+        double *stage = c->stage;
         KParams<float> p = make_params<float>(c, b, b);
         p.src += (size_t)y0 * c->pitch;
         p.nyl = ny;
@@ -894,8 +914,6 @@ static int download_buffer(lbm_ctx *c, int b, double *f, int y0 = 0, int ny = -1
             c->launches += 1;
             CU(cudaMemcpyAsync(f + (size_t)i * ny * nx, stage, (size_t)ny * nx * 8, cudaMemcpyDeviceToHost, c->stream));
         }
-        CU(cudaStreamSynchronize(c->stream));
-        CU(cudaFree(stage));
     }
     CU(cudaStreamSynchronize(c->stream));
     return 0;
@@ -916,10 +934,12 @@ int lbm_download_f_collision(lbm_ctx *c, double *f) {
     if (c->state == ST_COLLIDED) {
         int rc = wait_comm(c);
         if (rc) return rc;
-        return download_buffer(c, c->cur, f);
+        rc = download_buffer(c, c->cur, f);
+        return rc ? rc : p2p_check(c);
     }
     if (!c->have_coll) return fail(LBM_ERR_STATE, "no f_collision: collide! has not run since the last upload");
-    return download_buffer(c, 1 - c->cur, f);
+    int rc = download_buffer(c, 1 - c->cur, f);
+    return rc ? rc : p2p_check(c);
 }
 
 static int check_rows(lbm_ctx *c, int y0, int ny) {
@@ -992,7 +1012,8 @@ int lbm_download_f_rows(lbm_ctx *c, int32_t y0, int32_t ny, double *f_rows) {
     if (rc) return rc;
     rc = materialize(c);
     if (rc) return rc;
-    return download_buffer(c, c->cur, f_rows, y0, ny);
+    rc = download_buffer(c, c->cur, f_rows, y0, ny);
+    return rc ? rc : p2p_check(c);
 }
 
 static void free_force(lbm_ctx *c) {
@@ -1005,7 +1026,7 @@ static void free_force(lbm_ctx *c) {
 
 // host double array -> device array of the context's element type
 static int upload_as_elt(lbm_ctx *c, const double *h, size_t n, void **dev) {
-    CU(cudaMalloc(dev, n * c->elt));
+    if (!*dev) CU(cudaMalloc(dev, n * c->elt));
     if (is64(c)) {
         CU(cudaMemcpy(*dev, h, n * 8, cudaMemcpyHostToDevice));
     } else {
@@ -1013,6 +1034,20 @@ static int upload_as_elt(lbm_ctx *c, const double *h, size_t n, void **dev) {
         for (size_t k = 0; k < n; ++k) tmp[k] = (float)h[k];
         CU(cudaMemcpy(*dev, tmp.data(), n * 4, cudaMemcpyHostToDevice));
     }
+    return 0;
+}
+
+// per-node 2-component field (static force / prescribed velocity).  A host closure re-evaluated every step lands here once
+// per step: the allocation (and the captured graphs, which only bake the pointer) are kept when the mode is unchanged.
+static int set_node_field(lbm_ctx *c, const double *F) {
+    if (c->force_mode == 2 && c->field) {
+        CU(cudaStreamSynchronize(c->stream));
+    } else {
+        free_force(c);
+    }
+    int rc = upload_as_elt(c, F, (size_t)2 * c->nyl * c->desc.nx, &c->field);
+    if (rc) return rc;
+    c->force_mode = 2;
     return 0;
 }
 
@@ -1038,22 +1073,14 @@ int lbm_set_force_field(lbm_ctx *c, const double *F) {
     CU(cudaSetDevice(c->desc.device));
     if (c->desc.collision == LBM_MRT && c->desc.ntau < 2) return fail(LBM_ERR_INVALID, "MRT forcing needs tau[1] (mrt.jl:94)");
     if (c->desc.collision == LBM_ITERATIVE_INIT) return fail(LBM_ERR_UNSUPPORTED, "IterativeInitializationCollisionModel has no force (iterative_initialization.jl:1-12)");
-    free_force(c);
-    int rc = upload_as_elt(c, F, (size_t)2 * c->nyl * c->desc.nx, &c->field);
-    if (rc) return rc;
-    c->force_mode = 2;
-    return 0;
+    return set_node_field(c, F);
 }
 
 int lbm_set_velocity_field(lbm_ctx *c, const double *u0) {
     if (!c || !u0) return fail(LBM_ERR_INVALID, "null argument");
     if (c->desc.collision != LBM_ITERATIVE_INIT) return fail(LBM_ERR_STATE, "lbm_set_velocity_field is for LBM_ITERATIVE_INIT contexts");
     CU(cudaSetDevice(c->desc.device));
-    free_force(c);
-    int rc = upload_as_elt(c, u0, (size_t)2 * c->nyl * c->desc.nx, &c->field);
-    if (rc) return rc;
-    c->force_mode = 2;
-    return 0;
+    return set_node_field(c, u0);
 }
 
 int lbm_set_force_separable(lbm_ctx *c, int64_t t0, int32_t nsteps, const double *fx_of_y, const double *fy_of_x) {
@@ -1148,6 +1175,7 @@ int lbm_step(lbm_ctx *c, int64_t t0, int64_t nsteps, double dt) {
     CU(cudaSetDevice(c->desc.device));
     int rc = check_force_window(c, t0, nsteps);
     if (rc) return rc;
+    if (c->p2p_failed) return p2p_check(c);
     CU(cudaEventRecord(c->ev_t0, c->stream));
     c->p2p_in_batch = false;
     if (c->p2p_on && c->opt_p2p) {
@@ -1213,6 +1241,12 @@ int lbm_halo_path(const lbm_ctx *c) { return !c || c->desc.world == 1 ? 0 : (c->
 
 int lbm_set_option(lbm_ctx *c, const char *key, int64_t value) {
     if (!c || !key) return fail(LBM_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(c->desc.device));
+    // "p2p" and "overlap" select the halo path: a collective choice (same value on every rank, before the next
+    // lbm_step); a pending exchange of the old path is drained first
+    int rc0 = wait_comm(c);
+    if (rc0) return rc0;
+    CU(cudaStreamSynchronize(c->stream));
     drop_graphs(c);
     if (!strcmp(key, "variant")) c->opt_variant = (int)value;
     else if (!strcmp(key, "graph")) c->opt_graph = (int)value;
@@ -1250,7 +1284,7 @@ int lbm_moments(lbm_ctx *c, double tau_visc, double *rho, double *ux, double *uy
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     for (int k = 0; k < 8; ++k) if (dev[k]) cudaFree(dev[k]);
     if (e != cudaSuccess) return fail(LBM_ERR_CUDA, "lbm_moments: %s", cudaGetErrorString(e));
-    return 0;
+    return p2p_check(c);
 }
 
 int lbm_reduce_errors(lbm_ctx *c, double tau_visc, double u_max, const lbm_sep_field *expected, double *out) {
@@ -1295,7 +1329,7 @@ int lbm_reduce_errors(lbm_ctx *c, double tau_visc, double u_max, const lbm_sep_f
     cudaFree(dev);
     if (e != cudaSuccess) return fail(LBM_ERR_CUDA, "lbm_reduce_errors: %s", cudaGetErrorString(e));
     memcpy(out, h, sizeof(h));
-    return 0;
+    return p2p_check(c);
 }
 
 int lbm_reduce(lbm_ctx *c, int32_t kind, double *out, int32_t n) {
@@ -1323,7 +1357,7 @@ int lbm_reduce(lbm_ctx *c, int32_t kind, double *out, int32_t n) {
     CU(cudaMemcpyAsync(h, c->red_out, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     for (int k = 0; k < n && k < 4; ++k) out[k] = h[k];
-    return 0;
+    return p2p_check(c);
 }
 
 }  // extern "C"

@@ -48,6 +48,8 @@ def make_context(q, cm, bcs, nx, ny, dtype="f64", arith="exact", comm=None, devi
 class DeviceState:
     """Device-resident populations + the collision model's force data."""
 
+    SEPARABLE_WINDOW = 2048  # lattice steps per separable force table (DecayingShearFlow(static), decaying_shear_flow.jl:131-147)
+
     def __init__(self, ctx, q, cm, comm=None):
         self.ctx, self.q, self.cm, self.comm = ctx, q, cm, comm
         self.y0, self.ny_local, self.nx, self.ny = ctx.y0, ctx.ny_local, ctx.nx, ctx.ny
@@ -58,8 +60,11 @@ class DeviceState:
     # -- force -------------------------------------------------------------------------------
     def max_batch(self):
         f = self.cm.force
-        if f is None or isinstance(f, LatticeForce):
+        if f is None:
             return 1 << 30
+        if isinstance(f, LatticeForce):
+            # a separable time-dependent table holds (NX + NY_local) values per step on host and device: bounded window
+            return self.SEPARABLE_WINDOW if f.kind() == "separable" else 1 << 30
         return 1  # opaque host closure: re-evaluated every step
 
     def prepare_force(self, t0, n, dt):
