@@ -217,6 +217,56 @@ int lbm_timer_start(lbm_ctx *ctx);
 int lbm_timer_stop(lbm_ctx *ctx, float *ms);
 int lbm_set_option(lbm_ctx *ctx, const char *key, int64_t value); /* tuning knobs, see DESIGN.md */
 
+/* ---- Batched small problems -------------------------------------------------------------------------------------
+ * The reference's parameter studies are loops of `simulate(problem, q; ...)` over tiny grids: 902 500 solves of a 3 x 5
+ * D2Q9 TRT Poiseuille flow, <= 5001 steps each (examples/notebooks/trt_magic_parameter.ipynb:30-103, 3 h on one thread),
+ * and the 950-point diagonal of the same table in poiseuille.ipynb (cell 9).  A lbm_batch holds `nbatch` independent
+ * problems of ONE shape -- the descriptor's grid, lattice, collision kind, dtype and boundary conditions -- each with
+ * its own relaxation times and uniform force; lbm_batch_run advances all of them with one launch that keeps every
+ * problem's populations on chip, evaluates the stop criterion there every `check_every` steps exactly as
+ * TrackHydrodynamicErrors.next! does (track_hydrodynamic_errors.jl:52-59: `mod(t, 100) == 0` -> should_stop!) and
+ * retires the problems that fire it.  Host population arrays are [problem][q][ny][nx] Float64 (one Julia `f[x, y, i]`
+ * after the other).  Problems must fit in shared memory (LBM_ERR_UNSUPPORTED otherwise; use one lbm_ctx per problem). */
+typedef struct lbm_batch lbm_batch;
+typedef enum {
+    LBM_BATCH_STOP_OFF = 0,
+    /* MeanVelocityStoppingCriteria (stopping_criteria.jl:17-55): |mean(u_x) / previous mean - 1| < tolerance */
+    LBM_BATCH_STOP_MEAN_VELOCITY = 1,
+    /* VelocityConvergenceStoppingCriteria (stopping_criteria.jl:71-115): sqrt(sum |u - u_old|^2) / sum |u_old|^2 < tolerance */
+    LBM_BATCH_STOP_VELOCITY_CONVERGENCE = 2
+} lbm_batch_stop_kind;
+typedef struct {
+    int32_t kind;        /* lbm_batch_stop_kind */
+    int32_t check_every; /* 100 in the reference */
+    double tolerance;
+} lbm_batch_stop;
+
+/* desc: nx, ny, lattice, dtype, collision (SRT / TRT / MRT), arith, ntau, n_bcs / bcs, device; world must be 1.  desc.tau
+ * is the initial value of every problem's relaxation times. */
+int lbm_batch_create(const lbm_desc *desc, int32_t nbatch, lbm_batch **out);
+void lbm_batch_destroy(lbm_batch *b);
+/* tau[nbatch][desc.ntau]: the collision model's relaxation times per problem (TRT(tau_s, tau_a, force), trt.jl:2-3) */
+int lbm_batch_set_tau(lbm_batch *b, const double *tau);
+/* fxy[nbatch][2]: uniform lattice force per problem (lattice_force(problem, ...), poiseuille.jl:72-82); NULL: no force */
+int lbm_batch_set_force_uniform(lbm_batch *b, const double *fxy);
+/* f_stream of problems [first, first + count); resets their step counter, stop flag and criterion memory */
+int lbm_batch_upload_f(lbm_batch *b, int32_t first, int32_t count, const double *f);
+/* the same initial f_stream [q][ny][nx] for every problem (initialize(strategy, q, problem) of a sweep over tau) */
+int lbm_batch_broadcast_f(lbm_batch *b, const double *f);
+int lbm_batch_download_f(lbm_batch *b, int32_t first, int32_t count, double *f);
+/* Every problem that has not stopped takes up to nsteps collide -> stream -> BC steps (lattice_boltzmann_model.jl:64-67);
+ * with a stop criterion it is evaluated whenever the problem's total step count t is a multiple of check_every and the
+ * problem freezes at that t when it fires.  Asynchronous.  stop == NULL: no criterion. */
+int lbm_batch_run(lbm_batch *b, int64_t nsteps, const lbm_batch_stop *stop);
+/* (synchronises) steps taken so far and whether the criterion has fired, per problem; either pointer may be NULL */
+int lbm_batch_status(lbm_batch *b, int32_t first, int32_t count, int64_t *steps_done, int32_t *stopped);
+/* lbm_reduce_errors for every problem: out[nbatch][16].  The separable tables of expected[8] are shared; coef
+ * [nbatch][8][3] = (c0, a[0], a[1]) per problem and field replaces the coefficients in expected (NULL: use those). */
+int lbm_batch_reduce_errors(lbm_batch *b, const double *tau_visc, const double *u_max, const lbm_sep_field expected[8],
+                            const double *coef, double *out);
+int lbm_batch_last_run_ms(lbm_batch *b, float *ms); /* CUDA-event time of the last lbm_batch_run */
+int64_t lbm_batch_kernel_launches(const lbm_batch *b);
+
 #ifdef __cplusplus
 }
 #endif

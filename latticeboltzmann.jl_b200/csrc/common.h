@@ -107,6 +107,49 @@ struct ErrorArgs {
     int nblocks;
 };
 
+// ----------------------------------------------------------------------------------------------
+// Batched small problems (lbm_batch_*): B independent problems of one shape, each with its own relaxation times and
+// uniform force, advanced by ONE persistent launch that keeps every problem's populations in shared memory for the
+// whole run and evaluates the stop criterion on chip (batch.cuh).
+// ----------------------------------------------------------------------------------------------
+template <typename T>
+struct BatchConsts {  // per problem; the same constants make_params derives from the relaxation times
+    T c[12];
+    T kn[5];
+    T shift;
+    T fx, fy;
+    int mrt_skip[5];
+    int forced;
+};
+
+// device-side names of lbm_batch_stop_kind (include/lbm_b200.h)
+enum { LBM_BATCH_STOP_NONE = 0, LBM_BATCH_STOP_MEAN_UX = 1, LBM_BATCH_STOP_VELOCITY_CHANGE = 2 };
+
+struct BatchParams {
+    int nx, nyg, nb;       // problem shape (nyg = NY: the BC helpers read p.nyg), number of problems
+    void *f;               // T [nb][Q][NY][NX]: f_stream of every problem
+    const void *consts;    // BatchConsts<T> [nb]
+    double *crit;          // stop-criterion state: [nb][2 N] previous velocity field (x-major pairs) or [nb][..][0] previous mean
+    long long *steps_done; // [nb] lattice steps taken so far (the reference's t)
+    int *stopped;          // [nb] the criterion fired at steps_done
+    long long nsteps;      // advance every running problem by at most this many steps
+    int stop_kind, check_every;
+    double tol;
+    int has_mw;            // some boundary condition is a moving wall (additive term table in shared memory)
+    int nbc, bc_sides;
+    BCd bc[LBM_MAX_BCS];
+};
+
+struct BatchErrorArgs {
+    const void *f;            // T [nb][Q][NY][NX]
+    int nx, ny, nb;
+    const double *tau_visc;   // [nb]
+    const double *u_max;      // [nb]
+    const double *coef;       // [nb][8][3]: c0, a0, a1 of every expected field
+    const double *tab;        // [8][2][nx + ny] shared separable tables (X then Y per field and term)
+    double *out;              // [nb][16]
+};
+
 // Launchers exported by one kernels_inst.cu instance.
 struct Ops {
     int lattice, arith;
@@ -140,6 +183,11 @@ struct Ops {
     // device-side hermite_based_equilibrium! from host-provided (rho, ux, uy, T) rows
     void (*init_eq64)(const KParams<double> &p, const double *rho, const double *ux, const double *uy, const double *T, cudaStream_t s);
     void (*init_eq32)(const KParams<float> &p, const double *rho, const double *ux, const double *uy, const double *T, cudaStream_t s);
+    // batched small problems: returns 0, or -1 when one problem does not fit in shared memory
+    int (*batch64)(int cm, const BatchParams &p, cudaStream_t s);
+    int (*batch32)(int cm, const BatchParams &p, cudaStream_t s);
+    void (*batch_errors64)(const BatchErrorArgs &e, cudaStream_t s);
+    void (*batch_errors32)(const BatchErrorArgs &e, cudaStream_t s);
     int (*init_constants)();  // uploads the __constant__ lattice tables on the current device
 };
 

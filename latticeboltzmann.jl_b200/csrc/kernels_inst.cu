@@ -126,8 +126,9 @@ __device__ __forceinline__ T cdot(T ux, T uy) {  // abscissae[1,i]*u[1] + abscis
 // ------------------------------------------------------------------------------------------
 // Which boundary condition (last in list order wins, boundary_conditions.jl:13-15) overwrites
 // population i at the 1-based global node (x1, y1)?  (cxo, cyo) = c[opposite(i)].  -1: none.
-template <typename T>
-__device__ __noinline__ int resolve_bc(const KParams<T> &p, int x1, int y1, int cxo, int cyo) {
+// (P: KParams<T> or BatchParams -- anything with nbc, bc[], nx, nyg)
+template <class P>
+__device__ __noinline__ int resolve_bc(const P &p, int x1, int y1, int cxo, int cyo) {
     for (int b = p.nbc - 1; b >= 0; --b) {
         const BCd &bc = p.bc[b];
         bool hit;
@@ -144,16 +145,16 @@ __device__ __noinline__ int resolve_bc(const KParams<T> &p, int x1, int y1, int 
     return -1;
 }
 
-template <typename T>
-__device__ __forceinline__ bool near_wall(const KParams<T> &p, int x, int yg) {
+template <class P>
+__device__ __forceinline__ bool near_wall(const P &p, int x, int yg) {
     const int m = p.bc_sides;
     return m != 0 && (((m >> LBM_WEST) & 1 && x < H) || ((m >> LBM_EAST) & 1 && x >= p.nx - H) ||
                       ((m >> LBM_SOUTH) & 1 && yg < H) || ((m >> LBM_NORTH) & 1 && yg >= p.nyg - H));
 }
 
 // f_new[x,y,i] = f_old[x,y,opp(i)] (+ 2 a_1 for a moving wall), a_1 = w_i * css * dot(rho_w u_w, c_i)
-template <int I, typename T>
-__device__ __forceinline__ T bounced(const KParams<T> &p, int b, T f_opp) {
+template <int I, typename T, class P>
+__device__ __forceinline__ T bounced(const P &p, int b, T f_opp) {
     if (p.bc[b].kind == LBM_BC_MOVING_WALL) {
         const LatConst<T> &c = LC<T>();
         const T ax = T(p.bc[b].ax), ay = T(p.bc[b].ay);
@@ -325,8 +326,9 @@ __device__ __forceinline__ void feq_sym_asym(T rho, T ux, T uy, T u2, T drho, T 
 // ------------------------------------------------------------------------------------------
 // `emit(I, value)` receives each post-collision population as soon as it is known (it is stored
 // right away, so no second Q-sized array is live).
-template <int CM, typename T, class Emit>
-__device__ __forceinline__ void collide_node(const KParams<T> &p, const T (&f)[Q], bool forced, T Fx, T Fy, Emit &&emit) {
+// (P: KParams<T> or BatchConsts<T> -- anything with c[], kn[], shift, mrt_skip[])
+template <int CM, typename T, class P, class Emit>
+__device__ __forceinline__ void collide_node(const P &p, const T (&f)[Q], bool forced, T Fx, T Fy, Emit &&emit) {
     T rho, ux, uy, drho;
     rho_u(f, rho, ux, uy, drho);
     if constexpr (CM == LBM_ITERATIVE_INIT) {
@@ -687,11 +689,10 @@ __global__ void __launch_bounds__(256) k_ghosts(const __grid_constant__ KParams<
 template <typename T>
 struct NodeDiag { double rho, ux, uy, axx, axy, ayy; };
 
-template <typename T, bool PULL>
-__device__ __forceinline__ void node_fields(const KParams<T> &p, int x, int y, double &rho, double &ux, double &uy,
-                                            double &axx, double &axy, double &ayy) {
-    T f[Q];
-    load_node<T, PULL>(p, x, y, f);
+// rho, u and a_bar_2 = sum(f[idx] * hermite(Val{2}, c_idx, q)) (moments.jl:27-28, 90-92; left folds) of one node's
+// populations held in registers (Float32 storage: deviations, widened and shifted back first)
+template <typename T>
+__device__ __forceinline__ void fields_of(const T (&f)[Q], double &rho, double &ux, double &uy, double &axx, double &axy, double &ayy) {
     double g[Q];
     static_for<0, Q>([&](auto I) {
         constexpr int i = decltype(I)::value;
@@ -700,7 +701,6 @@ __device__ __forceinline__ void node_fields(const KParams<T> &p, int x, int y, d
     });
     double drho_unused;
     rho_u<double>(g, rho, ux, uy, drho_unused);
-    // a_bar_2 = sum(f[idx] * hermite(Val{2}, c_idx, q))  (moments.jl:27-28, 90-92), left fold
     const LatConst<double> &c = c_lat64;
     axx = g[0] * c.H2[0][0]; axy = g[0] * c.H2[0][1]; ayy = g[0] * c.H2[0][2];
     static_for<1, Q>([&](auto I) {
@@ -709,6 +709,14 @@ __device__ __forceinline__ void node_fields(const KParams<T> &p, int x, int y, d
         axy = axy + g[i] * c.H2[i][1];
         ayy = ayy + g[i] * c.H2[i][2];
     });
+}
+
+template <typename T, bool PULL>
+__device__ __forceinline__ void node_fields(const KParams<T> &p, int x, int y, double &rho, double &ux, double &uy,
+                                            double &axx, double &axy, double &ayy) {
+    T f[Q];
+    load_node<T, PULL>(p, x, y, f);
+    fields_of<T>(f, rho, ux, uy, axx, axy, ayy);
 }
 
 template <typename T, bool PULL>
@@ -792,6 +800,31 @@ __global__ void __launch_bounds__(256) k_reduce(const __grid_constant__ KParams<
     }
 }
 
+// One node's contribution to the 16 sums of TrackHydrodynamicErrors.next! (track_hydrodynamic_errors.jl:134-203):
+// rho, u, p = tr(P)/D, sigma as in k_moments, scaled to dimensionless units, against the expected fields e[8] =
+// rho, ux, uy, p, sxx, sxy, syx, syy.
+__device__ __forceinline__ void error_terms(double rho, double ux, double uy, double axx, double axy, double ayy, double tau,
+                                            double u_max, const double (&e)[8], double (&acc)[16]) {
+    const double den = 1 + 1 / (2 * tau), fac = 1 / (u_max * u_max);
+    const double exx = rho * (ux * ux), exy = rho * (ux * uy), eyy = rho * (uy * uy);
+    const double bxx = (axx + (1 / (2 * tau)) * exx) / den, byy = (ayy + (1 / (2 * tau)) * eyy) / den;
+    const double pr = ((bxx - rho * (ux * ux - 1)) + (byy - rho * (uy * uy - 1))) / 2;
+    double sxx = (axx - exx) / den, sxy = (axy - exy) / den, syy = (ayy - eyy) / den;
+    const double tr = (sxx + syy) / 2;
+    sxx = (sxx - tr) * fac; syy = (syy - tr) * fac; sxy = sxy * fac;
+    const double vx = ux / u_max, vy = uy / u_max;
+    acc[0] += (rho - e[0]) * (rho - e[0]);
+    acc[1] += (vx - e[1]) * (vx - e[1]) + (vy - e[2]) * (vy - e[2]);
+    acc[2] += e[1] * e[1] + e[2] * e[2];
+    acc[3] += (pr - e[3]) * (pr - e[3]);
+    acc[4] += e[3] * e[3];
+    acc[5] += (e[4] - sxx) * (e[4] - sxx); acc[6] += e[4] * e[4];
+    acc[7] += (e[5] - sxy) * (e[5] - sxy); acc[8] += e[5] * e[5];
+    acc[9] += (e[7] - syy) * (e[7] - syy); acc[10] += e[7] * e[7];
+    acc[11] += (e[6] - sxy) * (e[6] - sxy); acc[12] += e[6] * e[6];
+    acc[13] += rho; acc[14] += rho * (vx + vy); acc[15] += rho * (vx * vx + vy * vy);
+}
+
 // TrackHydrodynamicErrors.next! (track_hydrodynamic_errors.jl:114-203) entirely on the device: per node
 // rho, u, p = tr(P)/D, sigma as in k_moments, scaled to dimensionless units, compared with the problem's
 // analytic fields given in separable form; 16 sums, deterministic two-stage reduction.
@@ -804,34 +837,18 @@ __global__ void __launch_bounds__(256) k_errors(const __grid_constant__ KParams<
     for (int k = 0; k < 16; ++k) acc[k] = 0;
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
     const int W = p.nx + p.nyl;
-    const double tau = ea.tau_visc, den = 1 + 1 / (2 * tau), fac = 1 / (ea.u_max * ea.u_max);
+    const double tau = ea.tau_visc;
     for (int y = blockIdx.y * blockDim.y + threadIdx.y; y < p.nyl; y += gridDim.y * blockDim.y)
         for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < p.nx; x += gridDim.x * blockDim.x) {
             double rho, ux, uy, axx, axy, ayy;
             node_fields<T, PULL>(p, x, y, rho, ux, uy, axx, axy, ayy);
-            const double exx = rho * (ux * ux), exy = rho * (ux * uy), eyy = rho * (uy * uy);
-            const double bxx = (axx + (1 / (2 * tau)) * exx) / den, byy = (ayy + (1 / (2 * tau)) * eyy) / den;
-            const double pr = ((bxx - rho * (ux * ux - 1)) + (byy - rho * (uy * uy - 1))) / 2;
-            double sxx = (axx - exx) / den, sxy = (axy - exy) / den, syy = (ayy - eyy) / den;
-            const double tr = (sxx + syy) / 2;
-            sxx = (sxx - tr) * fac; syy = (syy - tr) * fac; sxy = sxy * fac;
-            const double vx = ux / ea.u_max, vy = uy / ea.u_max;
             double e[8];
 #pragma unroll
             for (int f = 0; f < 8; ++f) {
                 const double *t0 = ea.tab + (size_t)(2 * f) * W, *t1 = t0 + W;
                 e[f] = ea.c0[f] + ea.a[f][0] * (__ldg(t0 + x) * __ldg(t0 + p.nx + y)) + ea.a[f][1] * (__ldg(t1 + x) * __ldg(t1 + p.nx + y));
             }
-            acc[0] += (rho - e[0]) * (rho - e[0]);
-            acc[1] += (vx - e[1]) * (vx - e[1]) + (vy - e[2]) * (vy - e[2]);
-            acc[2] += e[1] * e[1] + e[2] * e[2];
-            acc[3] += (pr - e[3]) * (pr - e[3]);
-            acc[4] += e[3] * e[3];
-            acc[5] += (e[4] - sxx) * (e[4] - sxx); acc[6] += e[4] * e[4];
-            acc[7] += (e[5] - sxy) * (e[5] - sxy); acc[8] += e[5] * e[5];
-            acc[9] += (e[7] - syy) * (e[7] - syy); acc[10] += e[7] * e[7];
-            acc[11] += (e[6] - sxy) * (e[6] - sxy); acc[12] += e[6] * e[6];
-            acc[13] += rho; acc[14] += rho * (vx + vy); acc[15] += rho * (vx * vx + vy * vy);
+            error_terms(rho, ux, uy, axx, axy, ayy, tau, ea.u_max, e, acc);
         }
     __shared__ double sm[16][8];
     const int lane = tid & 31, warp = tid >> 5;
@@ -1134,6 +1151,8 @@ static void launch_init_eq(const KParams<T> &p, const double *rho, const double 
     k_init_eq<T><<<grid_for(p, block, p.nyl, p.nx), block, 0, s>>>(p, rho, ux, uy, Tm);
 }
 
+#include "batch.cuh"
+
 static const Ops ops = {
     LBM_LATTICE, LBM_FAST,
     &launch_step<double>, &launch_step<float>,
@@ -1147,6 +1166,8 @@ static const Ops ops = {
     &launch_errors<double>, &launch_errors<float>,
     &launch_import32, &launch_export32,
     &launch_init_eq<double>, &launch_init_eq<float>,
+    &launch_batch<double>, &launch_batch<float>,
+    &launch_batch_errors<double>, &launch_batch_errors<float>,
     &init_constants,
 };
 

@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -193,6 +194,37 @@ static T *origin(const lbm_ctx *c, int b) {
     return reinterpret_cast<T *>(c->buf[b]) + (long long)c->gy * c->pitch + c->gx;
 }
 
+// Collision constants derived from the relaxation times, already converted to T (KParams<T> and BatchConsts<T> carry
+// the same members):
+//   SRT: c[0] = 1 - 1/tau, c[1] = 1/tau, shift = tau
+//   TRT: c[0] = -(1/tau_s), c[1] = 1/tau_a, shift = tau_a
+//   MRT: c[2n] = 1 - 1/tau_n, c[2n+1] = 1/tau_n (n = 2..N), kn[n] = css^n / n!, shift = tau_2
+template <typename T, class P>
+static void fill_collision_consts(P &p, int collision, const double *tau, int ntau, const LatticeInfo &li) {
+    const double css = li.css;
+    switch (collision) {
+    case LBM_SRT:
+    case LBM_ITERATIVE_INIT:
+        p.c[0] = (T)(1 - 1 / tau[0]); p.c[1] = (T)(1 / tau[0]); p.shift = (T)tau[0];
+        break;
+    case LBM_TRT:
+        p.c[0] = (T)(-(1 / tau[0])); p.c[1] = (T)(1 / tau[1]); p.shift = (T)tau[1];
+        break;
+    default: {
+        static const double fact[5] = {1, 1, 2, 6, 24};
+        for (int n = 2; n <= li.N; ++n) {
+            const double tn = tau[n - 1];
+            p.c[2 * n] = (T)(1 - 1 / tn);
+            p.c[2 * n + 1] = (T)(1 / tn);
+            p.kn[n] = (T)(std::pow(css, (double)n) / fact[n]);
+            p.mrt_skip[n] = (tn == 1.0);
+        }
+        p.shift = (T)(ntau >= 2 ? tau[1] : 0.0);
+        break;
+    }
+    }
+}
+
 template <typename T>
 static KParams<T> make_params(const lbm_ctx *c, int src, int dst) {
     KParams<T> p;
@@ -213,29 +245,7 @@ static KParams<T> make_params(const lbm_ctx *c, int src, int dst) {
     p.nyg = c->desc.ny;
     p.row_a0 = 0; p.row_an = c->nyl; p.row_b0 = 0; p.nrows = c->nyl;
     p.wrap_y = c->desc.world == 1;
-    const double *tau = c->desc.tau;
-    const double css = c->li.css;
-    switch (c->desc.collision) {
-    case LBM_SRT:
-    case LBM_ITERATIVE_INIT:
-        p.c[0] = (T)(1 - 1 / tau[0]); p.c[1] = (T)(1 / tau[0]); p.shift = (T)tau[0];
-        break;
-    case LBM_TRT:
-        p.c[0] = (T)(-(1 / tau[0])); p.c[1] = (T)(1 / tau[1]); p.shift = (T)tau[1];
-        break;
-    default: {
-        static const double fact[5] = {1, 1, 2, 6, 24};
-        for (int n = 2; n <= c->li.N; ++n) {
-            const double tn = tau[n - 1];
-            p.c[2 * n] = (T)(1 - 1 / tn);
-            p.c[2 * n + 1] = (T)(1 / tn);
-            p.kn[n] = (T)(std::pow(css, (double)n) / fact[n]);
-            p.mrt_skip[n] = (tn == 1.0);
-        }
-        p.shift = (T)(c->desc.ntau >= 2 ? tau[1] : 0.0);
-        break;
-    }
-    }
+    fill_collision_consts<T>(p, c->desc.collision, c->desc.tau, c->desc.ntau, c->li);
     p.force_mode = c->force_mode;
     p.fx = (T)c->fx; p.fy = (T)c->fy;
     p.field = (const T *)c->field;
@@ -708,12 +718,10 @@ void lbm_destroy(lbm_ctx *c) {
     delete c;
 }
 
-int lbm_create(const lbm_desc *d, lbm_ctx **out) {
-    if (!d || !out) return fail(LBM_ERR_INVALID, "null argument");
-    *out = nullptr;
+// everything about a descriptor that does not depend on the decomposition (shared by lbm_create / lbm_batch_create)
+static int validate_desc(const lbm_desc *d, LatticeInfo &li) {
     if (d->abi_version != LBM_ABI_VERSION) return fail(LBM_ERR_INVALID, "abi_version %d != %d", d->abi_version, LBM_ABI_VERSION);
     if (d->nx < 1 || d->ny < 1) return fail(LBM_ERR_INVALID, "grid %dx%d", d->nx, d->ny);
-    LatticeInfo li;
     if (!lattice_info(d->lattice, li)) return fail(LBM_ERR_INVALID, "unknown lattice id %d", d->lattice);
     if (d->dtype != LBM_F64 && d->dtype != LBM_F32) return fail(LBM_ERR_INVALID, "dtype %d", d->dtype);
     if (d->collision < LBM_SRT || d->collision > LBM_ITERATIVE_INIT) return fail(LBM_ERR_INVALID, "collision %d", d->collision);
@@ -733,6 +741,15 @@ int lbm_create(const lbm_desc *d, lbm_ctx **out) {
             return fail(LBM_ERR_INVALID, "bc %d: kind %d", b, bc.kind);
         }
     }
+    return 0;
+}
+
+int lbm_create(const lbm_desc *d, lbm_ctx **out) {
+    if (!d || !out) return fail(LBM_ERR_INVALID, "null argument");
+    *out = nullptr;
+    LatticeInfo li;
+    int vrc = validate_desc(d, li);
+    if (vrc) return vrc;
     if (d->world < 1 || d->rank < 0 || d->rank >= d->world) return fail(LBM_ERR_INVALID, "rank %d / world %d", d->rank, d->world);
     const Ops *ops = get_ops(d->lattice, d->arith);
     if (!ops) return fail(LBM_ERR_UNSUPPORTED, "no kernels for lattice %d", d->lattice);
@@ -1359,5 +1376,315 @@ int lbm_reduce(lbm_ctx *c, int32_t kind, double *out, int32_t n) {
     for (int k = 0; k < n && k < 4; ++k) out[k] = h[k];
     return p2p_check(c);
 }
+
+
+// ----------------------------------------------------------------------------------------------
+// batched small problems (kernels: batch.cuh)
+// ----------------------------------------------------------------------------------------------
+}  // extern "C"
+
+struct lbm_batch {
+    lbm_desc desc;
+    LatticeInfo li;
+    const Ops *ops = nullptr;
+    int nb = 0, N = 0;
+    size_t elt = 8;
+    void *f = nullptr;        // T [nb][Q][NY][NX]
+    void *consts = nullptr;   // BatchConsts<T> [nb]
+    std::vector<unsigned char> h_consts;  // host copy (relaxation times and force are set by separate calls)
+    double *crit = nullptr;   // [nb][2 N]
+    long long *steps = nullptr;
+    int *stopped = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    long long launches = 0;
+};
+
+template <typename T>
+static BatchConsts<T> *consts_of(lbm_batch *b) { return reinterpret_cast<BatchConsts<T> *>(b->h_consts.data()); }
+
+template <typename T>
+static void batch_fill_tau(lbm_batch *b, const double *tau, int stride) {
+    BatchConsts<T> *k = consts_of<T>(b);
+    for (int i = 0; i < b->nb; ++i) fill_collision_consts<T>(k[i], b->desc.collision, tau + (size_t)i * stride, b->desc.ntau, b->li);
+}
+
+static int batch_upload_consts(lbm_batch *b) {
+    CU(cudaMemcpyAsync(b->consts, b->h_consts.data(), b->h_consts.size(), cudaMemcpyHostToDevice, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return 0;
+}
+
+static int batch_check_range(const lbm_batch *b, int first, int count) {
+    if (first < 0 || count < 0 || (long long)first + count > b->nb) return fail(LBM_ERR_INVALID, "problems [%d, %d) outside the batch of %d", first, first + count, b->nb);
+    return 0;
+}
+
+__global__ void k_replicate(unsigned char *dst, const unsigned char *src, size_t bytes, long long copies) {
+    // dst[c][i] = src[i], 16 bytes per thread where possible (bytes is a multiple of 4)
+    const size_t total = bytes * (size_t)copies / 4;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x)
+        reinterpret_cast<uint32_t *>(dst)[e] = reinterpret_cast<const uint32_t *>(src)[e % (bytes / 4)];
+}
+
+// reset the run state (step counter, stop flag, criterion memory) of problems [first, first + count)
+static int batch_reset(lbm_batch *b, int first, int count) {
+    CU(cudaMemsetAsync(b->steps + first, 0, (size_t)count * sizeof(long long), b->stream));
+    CU(cudaMemsetAsync(b->stopped + first, 0, (size_t)count * sizeof(int), b->stream));
+    CU(cudaMemsetAsync(b->crit + (size_t)first * 2 * b->N, 0, (size_t)count * 2 * b->N * sizeof(double), b->stream));
+    return 0;
+}
+
+extern "C" {
+
+void lbm_batch_destroy(lbm_batch *b) {
+    if (!b) return;
+    cudaSetDevice(b->desc.device);
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    for (void *p : {b->f, b->consts, (void *)b->crit, (void *)b->steps, (void *)b->stopped})
+        if (p) cudaFree(p);
+    if (b->ev0) cudaEventDestroy(b->ev0);
+    if (b->ev1) cudaEventDestroy(b->ev1);
+    if (b->stream) cudaStreamDestroy(b->stream);
+    delete b;
+}
+
+int lbm_batch_create(const lbm_desc *d, int32_t nbatch, lbm_batch **out) {
+    if (!d || !out) return fail(LBM_ERR_INVALID, "null argument");
+    *out = nullptr;
+    LatticeInfo li;
+    int rc = validate_desc(d, li);
+    if (rc) return rc;
+    if (nbatch < 1) return fail(LBM_ERR_INVALID, "nbatch %d", nbatch);
+    if (d->world != 1) return fail(LBM_ERR_UNSUPPORTED, "a batch lives on one GPU: shard the problems over ranks instead (world must be 1)");
+    if (d->collision == LBM_ITERATIVE_INIT) return fail(LBM_ERR_UNSUPPORTED, "LBM_ITERATIVE_INIT is not available in batches");
+    const Ops *ops = get_ops(d->lattice, d->arith);
+    if (!ops) return fail(LBM_ERR_UNSUPPORTED, "no kernels for lattice %d", d->lattice);
+    const long long N = (long long)d->nx * d->ny;
+    if (N * li.Q > 65535) return fail(LBM_ERR_UNSUPPORTED, "%d x %d nodes do not fit on chip: batches are for small problems, use one lbm_ctx per problem", d->nx, d->ny);
+    lbm_batch *b = new lbm_batch();
+    b->desc = *d; b->li = li; b->ops = ops; b->nb = nbatch; b->N = (int)N;
+    b->elt = d->dtype == LBM_F64 ? 8 : 4;
+    cudaError_t e = cudaSetDevice(d->device);
+    if (e != cudaSuccess) { delete b; return fail(LBM_ERR_CUDA, "cudaSetDevice(%d): %s", d->device, cudaGetErrorString(e)); }
+    auto bail = [&](int code) { lbm_batch_destroy(b); return code; };
+    if (ops->init_constants() != 0) return bail(fail(LBM_ERR_CUDA, "constant upload failed: %s", cudaGetErrorString(cudaGetLastError())));
+    const size_t csz = d->dtype == LBM_F64 ? sizeof(BatchConsts<double>) : sizeof(BatchConsts<float>);
+    const size_t fbytes = (size_t)nbatch * li.Q * N * b->elt;
+    if (cudaMalloc(&b->f, fbytes) != cudaSuccess || cudaMalloc(&b->consts, (size_t)nbatch * csz) != cudaSuccess ||
+        cudaMalloc(&b->crit, (size_t)nbatch * 2 * N * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&b->steps, (size_t)nbatch * sizeof(long long)) != cudaSuccess ||
+        cudaMalloc(&b->stopped, (size_t)nbatch * sizeof(int)) != cudaSuccess)
+        return bail(fail(LBM_ERR_NOMEM, "batch of %d problems (%zu bytes of populations): %s", nbatch, fbytes, cudaGetErrorString(cudaGetLastError())));
+    if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&b->ev0) != cudaSuccess ||
+        cudaEventCreate(&b->ev1) != cudaSuccess)
+        return bail(fail(LBM_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError())));
+    cudaMemsetAsync(b->f, 0, fbytes, b->stream);
+    rc = batch_reset(b, 0, nbatch);
+    if (rc) return bail(rc);
+    // every problem starts with the descriptor's relaxation times and no force
+    b->h_consts.assign((size_t)nbatch * csz, 0);
+    std::vector<double> tau((size_t)nbatch * d->ntau);
+    for (int i = 0; i < nbatch; ++i) memcpy(&tau[(size_t)i * d->ntau], d->tau, d->ntau * sizeof(double));
+    if (d->dtype == LBM_F64) batch_fill_tau<double>(b, tau.data(), d->ntau);
+    else batch_fill_tau<float>(b, tau.data(), d->ntau);
+    rc = batch_upload_consts(b);
+    if (rc) return bail(rc);
+    *out = b;
+    return 0;
+}
+
+int lbm_batch_set_tau(lbm_batch *b, const double *tau) {
+    if (!b || !tau) return fail(LBM_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(b->desc.device));
+    for (size_t i = 0; i < (size_t)b->nb * b->desc.ntau; ++i)
+        if (!(tau[i] == tau[i]) || tau[i] == 0.0) return fail(LBM_ERR_INVALID, "tau[%zu][%zu] = %g", i / b->desc.ntau, i % b->desc.ntau, tau[i]);
+    if (b->desc.dtype == LBM_F64) batch_fill_tau<double>(b, tau, b->desc.ntau);
+    else batch_fill_tau<float>(b, tau, b->desc.ntau);
+    return batch_upload_consts(b);
+}
+
+int lbm_batch_set_force_uniform(lbm_batch *b, const double *fxy) {
+    if (!b) return fail(LBM_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(b->desc.device));
+    if (fxy && b->desc.collision == LBM_MRT && b->desc.ntau < 2) return fail(LBM_ERR_INVALID, "MRT forcing needs tau[1] (mrt.jl:94)");
+    for (int i = 0; i < b->nb; ++i) {
+        if (b->desc.dtype == LBM_F64) {
+            BatchConsts<double> &k = consts_of<double>(b)[i];
+            k.forced = fxy != nullptr; k.fx = fxy ? fxy[2 * i] : 0; k.fy = fxy ? fxy[2 * i + 1] : 0;
+        } else {
+            BatchConsts<float> &k = consts_of<float>(b)[i];
+            k.forced = fxy != nullptr; k.fx = fxy ? (float)fxy[2 * i] : 0; k.fy = fxy ? (float)fxy[2 * i + 1] : 0;
+        }
+    }
+    return batch_upload_consts(b);
+}
+
+// host Float64 [count][q][ny][nx] <-> device storage (Float32 batches store f - w)
+static int batch_copy_f(lbm_batch *b, int first, int count, double *f, bool upload) {
+    const size_t per = (size_t)b->li.Q * b->N;
+    if (count == 0) return 0;
+    if (b->elt == 8) {
+        double *dev = reinterpret_cast<double *>(b->f) + (size_t)first * per;
+        CU(cudaMemcpyAsync(upload ? (void *)dev : (void *)f, upload ? (const void *)f : (const void *)dev, (size_t)count * per * 8,
+                           upload ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, b->stream));
+        CU(cudaStreamSynchronize(b->stream));
+        return 0;
+    }
+    float *dev = reinterpret_cast<float *>(b->f) + (size_t)first * per;
+    const size_t chunk = std::max<size_t>(1, ((size_t)8 << 20) / per);  // problems per staging chunk
+    std::vector<float> tmp(std::min<size_t>(chunk, count) * per);
+    for (size_t c0 = 0; c0 < (size_t)count; c0 += chunk) {
+        const size_t n = std::min<size_t>(chunk, count - c0);
+        if (upload) {
+            for (size_t p = 0; p < n; ++p)
+                for (int i = 0; i < b->li.Q; ++i)
+                    for (int k = 0; k < b->N; ++k) tmp[(p * b->li.Q + i) * b->N + k] = (float)(f[((c0 + p) * b->li.Q + i) * b->N + k] - b->li.w[i]);
+            CU(cudaMemcpyAsync(dev + c0 * per, tmp.data(), n * per * 4, cudaMemcpyHostToDevice, b->stream));
+            CU(cudaStreamSynchronize(b->stream));
+        } else {
+            CU(cudaMemcpyAsync(tmp.data(), dev + c0 * per, n * per * 4, cudaMemcpyDeviceToHost, b->stream));
+            CU(cudaStreamSynchronize(b->stream));
+            for (size_t p = 0; p < n; ++p)
+                for (int i = 0; i < b->li.Q; ++i)
+                    for (int k = 0; k < b->N; ++k) f[((c0 + p) * b->li.Q + i) * b->N + k] = (double)tmp[(p * b->li.Q + i) * b->N + k] + b->li.w[i];
+        }
+    }
+    return 0;
+}
+
+int lbm_batch_upload_f(lbm_batch *b, int32_t first, int32_t count, const double *f) {
+    if (!b || !f) return fail(LBM_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(b->desc.device));
+    int rc = batch_check_range(b, first, count);
+    if (rc) return rc;
+    rc = batch_copy_f(b, first, count, const_cast<double *>(f), true);
+    return rc ? rc : batch_reset(b, first, count);
+}
+
+int lbm_batch_broadcast_f(lbm_batch *b, const double *f) {
+    if (!b || !f) return fail(LBM_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(b->desc.device));
+    int rc = batch_copy_f(b, 0, 1, const_cast<double *>(f), true);
+    if (rc) return rc;
+    if (b->nb > 1) {
+        const size_t bytes = (size_t)b->li.Q * b->N * b->elt;
+        k_replicate<<<2048, 256, 0, b->stream>>>((unsigned char *)b->f + bytes, (const unsigned char *)b->f, bytes, (long long)b->nb - 1);
+        b->launches += 1;
+        CU(cudaGetLastError());
+    }
+    return batch_reset(b, 0, b->nb);
+}
+
+int lbm_batch_download_f(lbm_batch *b, int32_t first, int32_t count, double *f) {
+    if (!b || !f) return fail(LBM_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(b->desc.device));
+    int rc = batch_check_range(b, first, count);
+    if (rc) return rc;
+    return batch_copy_f(b, first, count, f, false);
+}
+
+int lbm_batch_run(lbm_batch *b, int64_t nsteps, const lbm_batch_stop *stop) {
+    if (!b) return fail(LBM_ERR_INVALID, "null argument");
+    if (nsteps < 0) return fail(LBM_ERR_INVALID, "nsteps %lld", (long long)nsteps);
+    CU(cudaSetDevice(b->desc.device));
+    BatchParams p;
+    memset(&p, 0, sizeof(p));
+    p.nx = b->desc.nx; p.nyg = b->desc.ny; p.nb = b->nb;
+    p.f = b->f; p.consts = b->consts; p.crit = b->crit; p.steps_done = b->steps; p.stopped = b->stopped;
+    p.nsteps = nsteps;
+    if (stop && stop->kind != LBM_BATCH_STOP_NONE) {
+        if (stop->kind != LBM_BATCH_STOP_MEAN_UX && stop->kind != LBM_BATCH_STOP_VELOCITY_CHANGE) return fail(LBM_ERR_INVALID, "stop kind %d", stop->kind);
+        if (stop->check_every < 1) return fail(LBM_ERR_INVALID, "check_every %d", stop->check_every);
+        p.stop_kind = stop->kind; p.check_every = stop->check_every; p.tol = stop->tolerance;
+    } else {
+        p.check_every = 1;
+    }
+    p.nbc = b->desc.n_bcs;
+    for (int k = 0; k < p.nbc; ++k) {
+        const lbm_bc &s = b->desc.bcs[k];
+        BCd &d = p.bc[k];
+        d.kind = s.kind; d.dir = s.direction;
+        d.x0 = s.x0; d.x1 = s.x1; d.y0 = s.y0; d.y1 = s.y1;
+        d.ax = s.rho * s.u[0]; d.ay = s.rho * s.u[1];
+        p.bc_sides |= 1 << s.direction;
+        if (s.kind == LBM_BC_MOVING_WALL) p.has_mw = 1;
+    }
+    CU(cudaEventRecord(b->ev0, b->stream));
+    const int rc = b->desc.dtype == LBM_F64 ? b->ops->batch64(b->desc.collision, p, b->stream) : b->ops->batch32(b->desc.collision, p, b->stream);
+    if (rc == -1) return fail(LBM_ERR_UNSUPPORTED, "a %d x %d problem does not fit in shared memory", p.nx, p.nyg);
+    if (rc) return fail(LBM_ERR_CUDA, "batch launch configuration failed: %s", cudaGetErrorString(cudaGetLastError()));
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(b->ev1, b->stream));
+    b->launches += 1;
+    b->timed = true;
+    return 0;
+}
+
+int lbm_batch_status(lbm_batch *b, int32_t first, int32_t count, int64_t *steps_done, int32_t *stopped) {
+    if (!b) return fail(LBM_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(b->desc.device));
+    int rc = batch_check_range(b, first, count);
+    if (rc) return rc;
+    static_assert(sizeof(long long) == sizeof(int64_t), "int64");
+    if (steps_done) CU(cudaMemcpyAsync(steps_done, b->steps + first, (size_t)count * 8, cudaMemcpyDeviceToHost, b->stream));
+    if (stopped) CU(cudaMemcpyAsync(stopped, b->stopped + first, (size_t)count * 4, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return 0;
+}
+
+int lbm_batch_reduce_errors(lbm_batch *b, const double *tau_visc, const double *u_max, const lbm_sep_field *expected,
+                            const double *coef, double *out) {
+    if (!b || !tau_visc || !u_max || !expected || !out) return fail(LBM_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(b->desc.device));
+    const int nx = b->desc.nx, ny = b->desc.ny, W = nx + ny, nb = b->nb;
+    for (int i = 0; i < nb; ++i)
+        if (!(tau_visc[i] > 0) || !(u_max[i] > 0)) return fail(LBM_ERR_INVALID, "problem %d: tau_visc %g, u_max %g", i, tau_visc[i], u_max[i]);
+    std::vector<double> tab((size_t)16 * W, 1.0), cf;
+    for (int f = 0; f < 8; ++f)
+        for (int k = 0; k < 2; ++k) {
+            double *t = tab.data() + (size_t)(2 * f + k) * W;
+            if (expected[f].x[k]) memcpy(t, expected[f].x[k], (size_t)nx * 8);
+            if (expected[f].y[k]) memcpy(t + nx, expected[f].y[k], (size_t)ny * 8);
+        }
+    if (!coef) {  // the same coefficients for every problem
+        cf.resize((size_t)nb * 24);
+        for (int i = 0; i < nb; ++i)
+            for (int f = 0; f < 8; ++f) { cf[(size_t)i * 24 + 3 * f] = expected[f].c0; cf[(size_t)i * 24 + 3 * f + 1] = expected[f].a[0]; cf[(size_t)i * 24 + 3 * f + 2] = expected[f].a[1]; }
+        coef = cf.data();
+    }
+    double *dev = nullptr;
+    const size_t n_in = tab.size() + (size_t)nb * (24 + 2), n_all = n_in + (size_t)nb * 16;
+    CU(cudaMalloc(&dev, n_all * 8));
+    double *d_tab = dev, *d_coef = d_tab + tab.size(), *d_tau = d_coef + (size_t)nb * 24, *d_um = d_tau + nb, *d_out = d_um + nb;
+    cudaError_t e = cudaMemcpyAsync(d_tab, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, b->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_coef, coef, (size_t)nb * 24 * 8, cudaMemcpyHostToDevice, b->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_tau, tau_visc, (size_t)nb * 8, cudaMemcpyHostToDevice, b->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_um, u_max, (size_t)nb * 8, cudaMemcpyHostToDevice, b->stream);
+    if (e == cudaSuccess) {
+        BatchErrorArgs ea{b->f, nx, ny, nb, d_tau, d_um, d_coef, d_tab, d_out};
+        if (b->desc.dtype == LBM_F64) b->ops->batch_errors64(ea, b->stream);
+        else b->ops->batch_errors32(ea, b->stream);
+        b->launches += 1;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, (size_t)nb * 16 * 8, cudaMemcpyDeviceToHost, b->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
+    cudaFree(dev);
+    if (e != cudaSuccess) return fail(LBM_ERR_CUDA, "lbm_batch_reduce_errors: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int lbm_batch_last_run_ms(lbm_batch *b, float *ms) {
+    if (!b || !ms) return fail(LBM_ERR_INVALID, "null argument");
+    if (!b->timed) return fail(LBM_ERR_STATE, "no lbm_batch_run has been issued");
+    CU(cudaSetDevice(b->desc.device));
+    CU(cudaEventSynchronize(b->ev1));
+    CU(cudaEventElapsedTime(ms, b->ev0, b->ev1));
+    return 0;
+}
+
+int64_t lbm_batch_kernel_launches(const lbm_batch *b) { return b ? b->launches : 0; }
 
 }  // extern "C"

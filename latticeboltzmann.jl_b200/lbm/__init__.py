@@ -8,6 +8,7 @@ benchmarks and notebooks use); Julia's `f!` is spelled `f_`.  Arrays are Float64
 """
 from . import _abi
 from ._abi import LbmError
+from .batch import BatchResult, simulate_many
 from .boundary_conditions import (BoundaryCondition, BounceBack, Direction, East, MovingWall, North, South, West)
 from .collision_models import (MRT, SRT, TRT, CollisionModel, IterativeInitializationCollisionModel, LatticeForce,
                                TRT_Lambda)

@@ -38,7 +38,11 @@ EXPORTS = [
     "lbm_collide", "lbm_stream", "lbm_apply_bcs", "lbm_step", "lbm_sync", "lbm_moments", "lbm_reduce",
     "lbm_reduce_errors",
     "lbm_kernel_launches", "lbm_halo_path", "lbm_last_step_ms", "lbm_timer_start", "lbm_timer_stop", "lbm_set_option",
+    "lbm_batch_create", "lbm_batch_destroy", "lbm_batch_set_tau", "lbm_batch_set_force_uniform", "lbm_batch_upload_f",
+    "lbm_batch_broadcast_f", "lbm_batch_download_f", "lbm_batch_run", "lbm_batch_status", "lbm_batch_reduce_errors",
+    "lbm_batch_last_run_ms", "lbm_batch_kernel_launches",
 ]
+BATCH_STOP_OFF, BATCH_STOP_MEAN_VELOCITY, BATCH_STOP_VELOCITY_CONVERGENCE = 0, 1, 2
 
 
 class LbmError(RuntimeError):
@@ -55,6 +59,10 @@ class lbm_bc(C.Structure):
 
 class lbm_sep_field(C.Structure):
     _fields_ = [("c0", C.c_double), ("a", C.c_double * 2), ("x", C.c_void_p * 2), ("y", C.c_void_p * 2)]
+
+
+class lbm_batch_stop(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("check_every", C.c_int32), ("tolerance", C.c_double)]
 
 
 class lbm_desc(C.Structure):
@@ -118,6 +126,20 @@ def lib():
     l.lbm_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     l.lbm_timer_start.argtypes = [vp]
     l.lbm_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
+    l.lbm_batch_create.argtypes = [C.POINTER(lbm_desc), C.c_int32, C.POINTER(vp)]
+    l.lbm_batch_destroy.argtypes = [vp]
+    l.lbm_batch_destroy.restype = None
+    l.lbm_batch_set_tau.argtypes = [vp, vp]
+    l.lbm_batch_set_force_uniform.argtypes = [vp, vp]
+    l.lbm_batch_upload_f.argtypes = [vp, C.c_int32, C.c_int32, vp]
+    l.lbm_batch_broadcast_f.argtypes = [vp, vp]
+    l.lbm_batch_download_f.argtypes = [vp, C.c_int32, C.c_int32, vp]
+    l.lbm_batch_run.argtypes = [vp, C.c_int64, C.POINTER(lbm_batch_stop)]
+    l.lbm_batch_status.argtypes = [vp, C.c_int32, C.c_int32, vp, vp]
+    l.lbm_batch_reduce_errors.argtypes = [vp, vp, vp, C.POINTER(lbm_sep_field), vp, vp]
+    l.lbm_batch_last_run_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    l.lbm_batch_kernel_launches.argtypes = [vp]
+    l.lbm_batch_kernel_launches.restype = C.c_int64
     if l.lbm_abi_version() != LBM_ABI_VERSION:
         raise LbmError(-1, f"ABI version mismatch: library {l.lbm_abi_version()} != binding {LBM_ABI_VERSION}")
     _lib = l
@@ -158,34 +180,41 @@ def _as_f64(a, shape=None):
     return a
 
 
+def make_desc(nx, ny, lattice, collision, tau, bcs=(), dtype=F64, arith=ARITH_EXACT, device=0, rank=0, world=1,
+              nccl_id=None):
+    """lbm_desc: everything `LatticeBoltzmannModel(problem, q; collision_model, ...)` fixes."""
+    d = lbm_desc()
+    d.abi_version = LBM_ABI_VERSION
+    d.nx, d.ny = int(nx), int(ny)
+    d.lattice = LATTICE_IDS[lattice] if isinstance(lattice, str) else int(lattice)
+    d.dtype, d.collision, d.arith = int(dtype), int(collision), int(arith)
+    tau = [float(t) for t in np.atleast_1d(tau)]
+    if len(tau) > LBM_MAX_TAU:
+        raise ValueError("too many relaxation times")
+    d.ntau = len(tau)
+    for i, t in enumerate(tau):
+        d.tau[i] = t
+    bcs = list(bcs)
+    if len(bcs) > LBM_MAX_BCS:
+        raise ValueError(f"at most {LBM_MAX_BCS} boundary conditions")
+    d.n_bcs = len(bcs)
+    for i, b in enumerate(bcs):
+        d.bcs[i] = b
+    d.device, d.rank, d.world = int(device), int(rank), int(world)
+    if world > 1:
+        if nccl_id is None or len(nccl_id) != LBM_NCCL_ID_BYTES:
+            raise ValueError("world > 1 needs the 128-byte NCCL id from rank 0")
+        C.memmove(d.nccl_id, nccl_id, LBM_NCCL_ID_BYTES)
+    return d
+
+
 class Context:
     """One lbm_ctx.  Population arrays are numpy Float64 of shape (NX, NY_local, Q) in Fortran
     order -- the memory order of Julia's `f[x, y, i]`."""
 
     def __init__(self, nx, ny, lattice, collision, tau, bcs=(), dtype=F64, arith=ARITH_EXACT, device=0,
                  rank=0, world=1, nccl_id=None):
-        d = lbm_desc()
-        d.abi_version = LBM_ABI_VERSION
-        d.nx, d.ny = int(nx), int(ny)
-        d.lattice = LATTICE_IDS[lattice] if isinstance(lattice, str) else int(lattice)
-        d.dtype, d.collision, d.arith = int(dtype), int(collision), int(arith)
-        tau = [float(t) for t in np.atleast_1d(tau)]
-        if len(tau) > LBM_MAX_TAU:
-            raise ValueError("too many relaxation times")
-        d.ntau = len(tau)
-        for i, t in enumerate(tau):
-            d.tau[i] = t
-        bcs = list(bcs)
-        if len(bcs) > LBM_MAX_BCS:
-            raise ValueError(f"at most {LBM_MAX_BCS} boundary conditions")
-        d.n_bcs = len(bcs)
-        for i, b in enumerate(bcs):
-            d.bcs[i] = b
-        d.device, d.rank, d.world = int(device), int(rank), int(world)
-        if world > 1:
-            if nccl_id is None or len(nccl_id) != LBM_NCCL_ID_BYTES:
-                raise ValueError("world > 1 needs the 128-byte NCCL id from rank 0")
-            C.memmove(d.nccl_id, nccl_id, LBM_NCCL_ID_BYTES)
+        d = make_desc(nx, ny, lattice, collision, tau, bcs, dtype, arith, device, rank, world, nccl_id)
         self._h = C.c_void_p()
         self.desc = d
         check(lib().lbm_create(C.byref(d), C.byref(self._h)))
@@ -363,3 +392,125 @@ class Context:
 
     def set_option(self, key, value):
         check(lib().lbm_set_option(self._h, key.encode(), int(value)))
+
+
+def _sep_fields(expected, nx, ny):
+    """expected: 8 tuples (c0, [(a, X or None, Y or None), ...up to 2 terms]) -> (lbm_sep_field * 8, keep-alive list)"""
+    arr = (lbm_sep_field * 8)()
+    keep = []
+    for f, (c0, terms) in enumerate(expected):
+        arr[f].c0 = float(c0)
+        if len(terms) > 2:
+            raise ValueError("at most two separable terms per field")
+        for k, (a, X, Y) in enumerate(terms):
+            arr[f].a[k] = float(a)
+            for name, tab, n in (("x", X, nx), ("y", Y, ny)):
+                if tab is not None:
+                    t = np.ascontiguousarray(tab, dtype=np.float64)
+                    if t.shape != (n,):
+                        raise ValueError(f"separable table '{name}' must have {n} entries")
+                    keep.append(t)
+                    getattr(arr[f], name)[k] = t.ctypes.data
+    return arr, keep
+
+
+class Batch:
+    """One lbm_batch: `nbatch` independent problems of one shape, advanced by a single launch that keeps every problem
+    on chip.  Population arrays are numpy Float64 of shape (NX, NY, Q, nbatch) in Fortran order (problem after problem,
+    each in the memory order of Julia's `f[x, y, i]`)."""
+
+    def __init__(self, nbatch, nx, ny, lattice, collision, tau, bcs=(), dtype=F64, arith=ARITH_EXACT, device=0):
+        d = make_desc(nx, ny, lattice, collision, tau, bcs, dtype, arith, device)
+        self._h = C.c_void_p()
+        self.desc = d
+        check(lib().lbm_batch_create(C.byref(d), int(nbatch), C.byref(self._h)))
+        self.nbatch, self.nx, self.ny, self.ntau = int(nbatch), d.nx, d.ny, d.ntau
+        self.Q = lattice_info(d.lattice)["Q"]
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().lbm_batch_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_tau(self, tau):
+        """tau: (nbatch, ntau)"""
+        t = np.ascontiguousarray(tau, dtype=np.float64)
+        if t.shape != (self.nbatch, self.ntau):
+            raise ValueError(f"relaxation times must have shape ({self.nbatch}, {self.ntau})")
+        check(lib().lbm_batch_set_tau(self._h, t.ctypes.data))
+
+    def set_force_uniform(self, fxy):
+        """fxy: (nbatch, 2) lattice force per problem, or None"""
+        if fxy is None:
+            check(lib().lbm_batch_set_force_uniform(self._h, None))
+            return
+        f = np.ascontiguousarray(fxy, dtype=np.float64)
+        if f.shape != (self.nbatch, 2):
+            raise ValueError(f"forces must have shape ({self.nbatch}, 2)")
+        check(lib().lbm_batch_set_force_uniform(self._h, f.ctypes.data))
+
+    def upload_f(self, f, first=0):
+        """f: (NX, NY, Q, count) Fortran-ordered"""
+        f = np.asfortranarray(f, dtype=np.float64)
+        if f.ndim != 4 or f.shape[:3] != (self.nx, self.ny, self.Q):
+            raise ValueError(f"expected (NX={self.nx}, NY={self.ny}, Q={self.Q}, count)")
+        check(lib().lbm_batch_upload_f(self._h, int(first), f.shape[3], f.ctypes.data))
+
+    def broadcast_f(self, f):
+        """f: (NX, NY, Q): the same initial f_stream for every problem"""
+        f = np.asfortranarray(f, dtype=np.float64)
+        if f.shape != (self.nx, self.ny, self.Q):
+            raise ValueError(f"expected (NX={self.nx}, NY={self.ny}, Q={self.Q})")
+        check(lib().lbm_batch_broadcast_f(self._h, f.ctypes.data))
+
+    def download_f(self, first=0, count=None):
+        count = self.nbatch - first if count is None else int(count)
+        out = np.empty((self.nx, self.ny, self.Q, count), dtype=np.float64, order="F")
+        check(lib().lbm_batch_download_f(self._h, int(first), count, out.ctypes.data))
+        return out
+
+    def run(self, nsteps, stop_kind=BATCH_STOP_OFF, check_every=100, tolerance=0.0):
+        st = lbm_batch_stop(int(stop_kind), int(check_every), float(tolerance))
+        check(lib().lbm_batch_run(self._h, int(nsteps), C.byref(st) if stop_kind else None))
+
+    def status(self, first=0, count=None):
+        """-> (steps_done int64[count], stopped bool[count]); synchronises"""
+        count = self.nbatch - first if count is None else int(count)
+        steps = np.empty(count, dtype=np.int64)
+        stopped = np.empty(count, dtype=np.int32)
+        check(lib().lbm_batch_status(self._h, int(first), count, steps.ctypes.data, stopped.ctypes.data))
+        return steps, stopped.astype(bool)
+
+    def reduce_errors(self, tau_visc, u_max, expected, coef=None):
+        """-> (nbatch, 16) sums of TrackHydrodynamicErrors.next! per problem.  expected as Context.reduce_errors (tables
+        shared by all problems); coef (nbatch, 8, 3) = per-problem (c0, a0, a1) of every field, or None."""
+        tv = np.ascontiguousarray(np.broadcast_to(np.asarray(tau_visc, dtype=np.float64), (self.nbatch,)))
+        um = np.ascontiguousarray(np.broadcast_to(np.asarray(u_max, dtype=np.float64), (self.nbatch,)))
+        arr, keep = _sep_fields(expected, self.nx, self.ny)
+        cf = None
+        if coef is not None:
+            cf = np.ascontiguousarray(coef, dtype=np.float64)
+            if cf.shape != (self.nbatch, 8, 3):
+                raise ValueError(f"coef must have shape ({self.nbatch}, 8, 3)")
+        out = np.empty((self.nbatch, 16), dtype=np.float64)
+        check(lib().lbm_batch_reduce_errors(self._h, tv.ctypes.data, um.ctypes.data, arr, cf.ctypes.data if cf is not None else None,
+                                            out.ctypes.data))
+        del keep
+        return out
+
+    def last_run_ms(self):
+        ms = C.c_float()
+        check(lib().lbm_batch_last_run_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    @property
+    def kernel_launches(self):
+        return int(lib().lbm_batch_kernel_launches(self._h))

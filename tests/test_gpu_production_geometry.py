@@ -131,7 +131,17 @@ def test_config_c2_full_size_4096_20_steps(oracle):
         if mode == "f64-exact":
             assert np.array_equal(got, want)
         assert rel_max(got, want) < tol, mode
-        assert rel_max(mo["ux"].T, ux) < tol and rel_max(mo["uy"].T, uy) < tol, mode
+        # velocities (|u| <= 4e-4 here): Float64 in lattice units against the unit lattice speed -- an error of 1e-12 in
+        # u is what a relative 1e-12 on the populations (f ~ w ~ 0.1 .. 0.4) can leave; bit-identical in exact mode --
+        # Float32 relative to max |u| (deviation storage keeps the small velocities resolved)
+        eu = max(np.abs(mo["ux"].T - ux).max(), np.abs(mo["uy"].T - uy).max())
+        umax = max(np.abs(ux).max(), np.abs(uy).max())
+        if mode == "f64-exact":
+            assert eu <= 1e-15 * umax, (mode, eu, umax)
+        elif dtype == _abi.F64:
+            assert eu < TOL64, (mode, eu, umax)
+        else:
+            assert eu < TOL32 * umax, (mode, eu, umax)
         del got, mo
 
 
