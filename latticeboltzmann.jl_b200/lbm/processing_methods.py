@@ -11,6 +11,7 @@ import warnings
 import numpy as np
 
 from . import _abi
+from .separable import separable_from_fields
 from .problems import (CouetteFlow, DecayingShearFlow, LidDrivenCavityFlow, PoiseuilleFlow, TGV,
                        TaylorGreenVortex)
 
@@ -166,6 +167,13 @@ class TrackHydrodynamicErrors(ProcessingMethodBase):
             Delta = xstep
         tau = q.speed_of_sound_squared * pr.lattice_viscosity()
         sep = pr.expected_separable(q, time, state.y0, state.ny_local) if self.device_norms else None
+        if sep is None and self.device_norms:
+            # no analytic separable form: recover one from the fields sampled on the grid (exact for rank <= 2)
+            X, Y = pr.grid(state.y0, state.ny_local)
+            e_ux, e_uy = pr.velocity(X, Y, time)
+            (e_sxx, e_sxy), (e_syx, e_syy) = pr.deviatoric_tensor(q, X, Y, time)
+            sep = separable_from_fields([np.asarray(a, dtype=np.float64) * np.ones_like(X) for a in (
+                pr.density(q, X, Y, time), e_ux, e_uy, pr.pressure(q, X, Y, time), e_sxx, e_sxy, e_syx, e_syy)])
         if sep is not None:
             # all 16 sums on the device (lbm_reduce_errors); nothing but scalars crosses PCIe
             s = state.allreduce(state.ctx.reduce_errors(tau, pr.u_max, sep))
