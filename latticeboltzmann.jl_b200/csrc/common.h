@@ -150,6 +150,23 @@ struct BatchErrorArgs {
     double *out;              // [nb][16]
 };
 
+// ----------------------------------------------------------------------------------------------
+// Persistent multi-step kernel (persist.cuh): one cooperative launch takes `nsteps` fused steps of a slab; the CTAs
+// are co-resident, each owns a contiguous range of nodes and synchronises only with the CTAs that own the rows within
+// the stencil's reach (and, on the slab edges, with the neighbouring GPUs through the peer-memory epoch flags).
+// ----------------------------------------------------------------------------------------------
+struct PersistArgs {
+    int nsteps;
+    long long step0;               // lattice step index of the first step (force tables are indexed by it)
+    unsigned long long *done;      // [grid] per-CTA count of completed steps of this launch (zeroed before the launch)
+    unsigned long long *edge_count;  // [2] CTAs that have finished the bottom / top boundary rows of the running step
+    unsigned long long *error;     // != 0: a wait gave up
+    unsigned long long epoch0;     // peer-memory epoch of the state the launch starts from
+    long long npc;                 // nodes per CTA
+    int nctas;                     // CTAs that own nodes
+    int n_bot, n_top;              // CTAs owning nodes of the bottom / top H rows
+};
+
 // Launchers exported by one kernels_inst.cu instance.
 struct Ops {
     int lattice, arith;
@@ -183,6 +200,12 @@ struct Ops {
     // device-side hermite_based_equilibrium! from host-provided (rho, ux, uy, T) rows
     void (*init_eq64)(const KParams<double> &p, const double *rho, const double *ux, const double *uy, const double *T, cudaStream_t s);
     void (*init_eq32)(const KParams<float> &p, const double *rho, const double *ux, const double *uy, const double *T, cudaStream_t s);
+    // persistent multi-step kernel: co-resident grid (CTAs, threads) for this <collision model, dtype>, 0 CTAs if the
+    // device cannot launch cooperatively; pa: src = current state, pb: the two buffers swapped
+    void (*persist_grid64)(int cm, bool p2p, int *ctas, int *threads);
+    void (*persist_grid32)(int cm, bool p2p, int *ctas, int *threads);
+    int (*persist64)(int cm, bool p2p, const KParams<double> &pa, const KParams<double> &pb, const PersistArgs &a, int ctas, int threads, cudaStream_t s);
+    int (*persist32)(int cm, bool p2p, const KParams<float> &pa, const KParams<float> &pb, const PersistArgs &a, int ctas, int threads, cudaStream_t s);
     // batched small problems: returns 0, or -1 when one problem does not fit in shared memory
     int (*batch64)(int cm, const BatchParams &p, cudaStream_t s);
     int (*batch32)(int cm, const BatchParams &p, cudaStream_t s);

@@ -170,13 +170,21 @@ __device__ __forceinline__ T bounced(const P &p, int b, T f_opp) {
 // PULL = false: f[i] = src[i, y, x]
 // PULL = true : f[i] = (stream + BCs)(src)[i, y, x]  i.e. src[i, y - c_y, x - c_x] unless a boundary
 //               condition overwrites it with src[opp(i), y, x].
-template <typename T, bool PULL>
+// COHERENT: read through L2 (ld.global.cg) instead of the non-coherent path -- the persistent kernel re-reads addresses
+//           that other CTAs rewrote since this SM last cached them.
+template <bool COHERENT, typename T>
+__device__ __forceinline__ T ld_pop(const T *q) {
+    if constexpr (COHERENT) return __ldcg(q);
+    else return __ldg(q);
+}
+
+template <typename T, bool PULL, bool COHERENT = false>
 __device__ __forceinline__ void load_node(const KParams<T> &p, int x, int y, T (&f)[Q]) {
     const unsigned n = (unsigned)y * (unsigned)p.pitch + (unsigned)x;
     static_for<0, Q>([&](auto I) {
         constexpr int i = decltype(I)::value;
-        if constexpr (PULL) f[i] = __ldg(p.srcp[i] + n);
-        else f[i] = __ldg(p.srcn[i] + n);
+        if constexpr (PULL) f[i] = ld_pop<COHERENT>(p.srcp[i] + n);
+        else f[i] = ld_pop<COHERENT>(p.srcn[i] + n);
     });
     if constexpr (PULL) {
         const int yg = p.y0g + y;
@@ -186,7 +194,7 @@ __device__ __forceinline__ void load_node(const KParams<T> &p, int x, int y, T (
                 constexpr int o = L::opp(i);
                 if constexpr (i != o) {
                     const int b = resolve_bc(p, x + 1, yg + 1, L::cx(o), L::cy(o));
-                    if (b >= 0) f[i] = bounced<i>(p, b, __ldg(p.srcn[o] + n));
+                    if (b >= 0) f[i] = bounced<i>(p, b, ld_pop<COHERENT>(p.srcn[o] + n));
                 }
             });
         }
@@ -388,43 +396,54 @@ __device__ __forceinline__ void collide_node(const P &p, const T (&f)[Q], bool f
         });
     } else {
         // regularised MRT (mrt.jl:56-118) with the symmetric tensors reduced to their unique
-        // components: a^(n) has n+1 of them, multiplicity C(n,k).
+        // components (a^(n) has n+1 of them, multiplicity C(n,k)) and the populations folded per opposite
+        // pair: H_n(-c) = (-1)^n H_n(c), so the even orders only need f_i + f_opp and the odd order f_i - f_opp --
+        // half the multiply-adds of the projection and of the reconstruction (the kernel is FMA-bound on the
+        // wide lattices: profiles/r02/ncu_summary.md).
         const LatConst<T> &c = LC<T>();
         T a2[3] = {T(0), T(0), T(0)}, a3[4] = {T(0), T(0), T(0), T(0)}, a4[5] = {T(0), T(0), T(0), T(0), T(0)};
-        if constexpr (NH >= 2) {
-            if (!p.mrt_skip[2]) {
-                static_for<0, Q>([&](auto I) {
-                    constexpr int i = decltype(I)::value;
+        const bool do2 = NH >= 2 && !p.mrt_skip[2], do3 = NH >= 3 && !p.mrt_skip[3], do4 = NH >= 4 && !p.mrt_skip[4];
+        if (do2 || do3 || do4) {
+            static_for<0, Q>([&](auto I) {
+                constexpr int i = decltype(I)::value;
+                constexpr int o = L::opp(i);
+                if constexpr (i <= o) {
+                    const T fs = (i == o) ? f[i] : f[i] + f[o];
+                    if constexpr (NH >= 2) {
+                        if (do2) {
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) a2[k] = a2[k] + f[i] * c.H2[i][k];
-                });
-            }
+                            for (int k = 0; k < 3; ++k) a2[k] = a2[k] + fs * c.H2[i][k];
+                        }
+                    }
+                    if constexpr (NH >= 3 && i != o) {  // H_3(0) = 0
+                        if (do3) {
+                            const T fa = f[i] - f[o];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) a3[k] = a3[k] + fa * c.H3[i][k];
+                        }
+                    }
+                    if constexpr (NH >= 4) {
+                        if (do4) {
+#pragma unroll
+                            for (int k = 0; k < 5; ++k) a4[k] = a4[k] + fs * c.H4[i][k];
+                        }
+                    }
+                }
+            });
+        }
+        if constexpr (NH >= 2) {
             const T e[3] = {rho * (ux * ux), rho * (ux * uy), rho * (uy * uy)};
             const T m[3] = {T(1), T(2), T(1)};
 #pragma unroll
             for (int k = 0; k < 3; ++k) a2[k] = (p.kn[2] * m[k]) * (p.c[4] * a2[k] + p.c[5] * e[k]);
         }
         if constexpr (NH >= 3) {
-            if (!p.mrt_skip[3]) {
-                static_for<0, Q>([&](auto I) {
-                    constexpr int i = decltype(I)::value;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) a3[k] = a3[k] + f[i] * c.H3[i][k];
-                });
-            }
             const T e[4] = {rho * (ux * ux * ux), rho * (ux * ux * uy), rho * (ux * uy * uy), rho * (uy * uy * uy)};
             const T m[4] = {T(1), T(3), T(3), T(1)};
 #pragma unroll
             for (int k = 0; k < 4; ++k) a3[k] = (p.kn[3] * m[k]) * (p.c[6] * a3[k] + p.c[7] * e[k]);
         }
         if constexpr (NH >= 4) {
-            if (!p.mrt_skip[4]) {
-                static_for<0, Q>([&](auto I) {
-                    constexpr int i = decltype(I)::value;
-#pragma unroll
-                    for (int k = 0; k < 5; ++k) a4[k] = a4[k] + f[i] * c.H4[i][k];
-                });
-            }
             const T x2 = ux * ux, y2 = uy * uy;
             const T e[5] = {rho * (x2 * x2), rho * (x2 * ux * uy), rho * (x2 * y2), rho * (ux * uy * y2), rho * (y2 * y2)};
             const T m[5] = {T(1), T(4), T(6), T(4), T(1)};
@@ -432,25 +451,36 @@ __device__ __forceinline__ void collide_node(const P &p, const T (&f)[Q], bool f
             for (int k = 0; k < 5; ++k) a4[k] = (p.kn[4] * m[k]) * (p.c[8] * a4[k] + p.c[9] * e[k]);
         }
         const T csrho = c.css * rho;
-        static_for<0, Q>([&](auto I) {  // mrt.jl:107-114
+        static_for<0, Q>([&](auto I) {  // mrt.jl:107-114, per pair: out_i = w (even + odd), out_opp = w (even - odd)
             constexpr int i = decltype(I)::value;
-            // shifted storage: sum(w H_n) = 0 for n <= N, so a_f is the projection of g and out - w = w (drho + ...)
-            T acc = (Shifted<T>::value ? drho : rho) + csrho * cdot<L::cx(i), L::cy(i)>(ux, uy);
-            if constexpr (NH >= 2) {
-                T hs = a2[0] * c.H2[i][0];
-                hs = hs + a2[1] * c.H2[i][1];
-                hs = hs + a2[2] * c.H2[i][2];
-                if constexpr (NH >= 3) {
+            constexpr int o = L::opp(i);
+            if constexpr (i <= o) {
+                // shifted storage: sum(w H_n) = 0 for n <= N, so a_f is the projection of g and out - w = w (drho + ...)
+                T even = Shifted<T>::value ? drho : rho;
+                T odd = csrho * cdot<L::cx(i), L::cy(i)>(ux, uy);
+                if constexpr (NH >= 2) {
+                    T hs = a2[0] * c.H2[i][0];
+                    hs = hs + a2[1] * c.H2[i][1];
+                    hs = hs + a2[2] * c.H2[i][2];
+                    if constexpr (NH >= 4) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) hs = hs + a3[k] * c.H3[i][k];
+                        for (int k = 0; k < 5; ++k) hs = hs + a4[k] * c.H4[i][k];
+                    }
+                    even = even + hs;
                 }
-                if constexpr (NH >= 4) {
+                if constexpr (NH >= 3 && i != o) {
+                    T ho = a3[0] * c.H3[i][0];
 #pragma unroll
-                    for (int k = 0; k < 5; ++k) hs = hs + a4[k] * c.H4[i][k];
+                    for (int k = 1; k < 4; ++k) ho = ho + a3[k] * c.H3[i][k];
+                    odd = odd + ho;
                 }
-                acc = acc + hs;
+                if constexpr (i == o) {
+                    emit(I, c.w[i] * (even + odd));
+                } else {
+                    emit(I, c.w[i] * (even + odd));
+                    emit(std::integral_constant<int, o>{}, c.w[i] * (even - odd));
+                }
             }
-            emit(I, c.w[i] * acc);
         });
     }
 }
@@ -868,23 +898,21 @@ __global__ void __launch_bounds__(256) k_errors(const __grid_constant__ KParams<
     }
 }
 
-__global__ void k_errors_final(const ErrorArgs ea) {
-    const int k = threadIdx.x;
-    if (k < 16) {
-        double v = 0;
-        for (int b = 0; b < ea.nblocks; ++b) v += ea.partials[(size_t)b * 16 + k];
-        ea.out[k] = v;
-    }
+// Second stage of the deterministic reductions: one warp per sum; lane l folds partials l, l + 32, ... in order, then a
+// fixed shuffle tree (same result on every run and every launch geometry of this stage).
+template <int NSUM>
+__device__ __forceinline__ void final_sum(const double *partials, int nblocks, double *out) {
+    const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (k >= NSUM) return;
+    double v = 0;
+    for (int b = lane; b < nblocks; b += 32) v += partials[(size_t)b * NSUM + k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) out[k] = v;
 }
+__global__ void __launch_bounds__(512) k_errors_final(const ErrorArgs ea) { final_sum<16>(ea.partials, ea.nblocks, ea.out); }
 
-__global__ void k_reduce_final(const ReduceArgs ra) {
-    const int k = threadIdx.x;
-    if (k < 4) {
-        double v = 0;
-        for (int b = 0; b < ra.nblocks; ++b) v += ra.partials[(size_t)b * 4 + k];
-        ra.out[k] = v;
-    }
-}
+__global__ void __launch_bounds__(128) k_reduce_final(const ReduceArgs ra) { final_sum<4>(ra.partials, ra.nblocks, ra.out); }
 
 // K7: device-side initialisation.  f_i = hermite_based_equilibrium!(q, rho, u, T)
 // (velocity_distribution_function/hermite.jl:10-33) from per-node fields [ny][nx] (Float64):
@@ -1120,7 +1148,7 @@ static void launch_reduce(bool pull, const KParams<T> &p, const ReduceArgs &r, c
     ra.nblocks = grid.x * grid.y;
     if (pull) k_reduce<T, true><<<grid, block, 0, s>>>(p, ra);
     else k_reduce<T, false><<<grid, block, 0, s>>>(p, ra);
-    k_reduce_final<<<1, 32, 0, s>>>(ra);
+    k_reduce_final<<<1, 128, 0, s>>>(ra);
 }
 
 template <typename T>
@@ -1133,7 +1161,7 @@ static void launch_errors(bool pull, const KParams<T> &p, const ErrorArgs &e, cu
     ea.nblocks = grid.x * grid.y;
     if (pull) k_errors<T, true><<<grid, block, 0, s>>>(p, ea);
     else k_errors<T, false><<<grid, block, 0, s>>>(p, ea);
-    k_errors_final<<<1, 32, 0, s>>>(ea);
+    k_errors_final<<<1, 512, 0, s>>>(ea);
 }
 
 static void launch_import32(const KParams<float> &p, const double *stage, int i, cudaStream_t s) {
@@ -1152,6 +1180,7 @@ static void launch_init_eq(const KParams<T> &p, const double *rho, const double 
 }
 
 #include "batch.cuh"
+#include "persist.cuh"
 
 static const Ops ops = {
     LBM_LATTICE, LBM_FAST,
@@ -1166,6 +1195,8 @@ static const Ops ops = {
     &launch_errors<double>, &launch_errors<float>,
     &launch_import32, &launch_export32,
     &launch_init_eq<double>, &launch_init_eq<float>,
+    &persist_grid<double>, &persist_grid<float>,
+    &launch_persist<double>, &launch_persist<float>,
     &launch_batch<double>, &launch_batch<float>,
     &launch_batch_errors<double>, &launch_batch_errors<float>,
     &init_constants,

@@ -175,6 +175,16 @@ struct lbm_ctx {
     bool timed = false;
     int opt_variant = 0;
     int opt_overlap = 1;
+    // persistent multi-step kernel (persist.cuh): 0 = off, 1 = whenever possible, 2 = automatic (launch-bound slabs)
+    int opt_persistent = 2;
+    int pg_ctas[2] = {-1, -1}, pg_threads[2] = {0, 0};  // co-resident grid of the plain / peer-memory variant (-1: not queried)
+    unsigned long long *pdone = nullptr;                // [error | edge_count[2] | pad | done[ctas]]
+    int pdone_ctas = 0;
+    bool persist_used = false;
+    unsigned long long persist_failed = 0;
+    // lbm_reduce_errors scratch: [separable tables | partials | out], kept between calls
+    double *err_dev = nullptr;
+    size_t err_doubles = 0;
     // reusable device staging for the Float32 import/export conversions (grown on demand, freed by lbm_destroy)
     double *stage = nullptr;
     size_t stage_bytes = 0;
@@ -437,6 +447,17 @@ static int p2p_connect(lbm_ctx *c) {
 // Called by every entry point that synchronises the stream and hands data back; the failure is sticky (lbm_step
 // refuses to continue from a state computed with stale ghost rows).
 static int p2p_check(lbm_ctx *c) {
+    if (c->persist_used) {  // did a wait inside a persistent launch give up?
+        if (!c->persist_failed) {
+            unsigned long long v = 0;
+            CU(cudaMemcpyAsync(&v, c->pdone, sizeof(v), cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            c->persist_failed = v;
+        }
+        if (c->persist_failed)
+            return fail(LBM_ERR_STATE, "a wait inside the persistent step kernel timed out (step %llu of its launch); the populations "
+                                       "of this context are invalid", c->persist_failed - 1);
+    }
     if (!c->p2p_on || (c->epoch == 0 && c->batch == 0)) return 0;
     if (!c->p2p_failed) {
         unsigned long long v = 0;
@@ -620,11 +641,90 @@ static int build_graph(lbm_ctx *c, int src) {
     return 0;
 }
 
+// ----------------------------------------------------------------------------------------------
+// persistent multi-step launch (persist.cuh)
+// ----------------------------------------------------------------------------------------------
+static const long long PERSIST_MIN_STEPS = 4;
+static const long long PERSIST_AUTO_NODES = 1LL << 21;  // automatic mode: slabs up to 2 Mi nodes (a step of <= ~50 us)
+
+static bool persist_ok(lbm_ctx *c, long long nsteps) {
+    if (!c->opt_persistent || nsteps < PERSIST_MIN_STEPS || c->desc.collision == LBM_ITERATIVE_INIT) return false;
+    const bool p2p = c->desc.world > 1;
+    if (p2p && !(c->p2p_on && c->opt_p2p && c->opt_overlap && c->nyl >= 2 * c->li.H + 1)) return false;
+    // two co-resident grids that wait for each other cannot share a GPU
+    if (p2p && (c->peer_up.info.device == c->desc.device || c->peer_dn.info.device == c->desc.device)) return false;
+    const long long N = (long long)c->desc.nx * c->nyl;
+    if (N >= (1LL << 32)) return false;
+    if (c->opt_persistent == 2) {
+        if (N > PERSIST_AUTO_NODES) return false;
+        // Float32 fast contexts on narrow lattices have the packed two-node kernel, which the persistent kernel does not
+        // use: only worth it where launches dominate
+        if (c->desc.dtype == LBM_F32 && c->desc.arith == LBM_ARITH_FAST && c->li.Q <= 13 && c->desc.collision != LBM_MRT &&
+            c->desc.nx % 2 == 0 && N > (1LL << 18))
+            return false;
+    }
+    int &ctas = c->pg_ctas[p2p ? 1 : 0];
+    if (ctas < 0) {
+        if (is64(c)) c->ops->persist_grid64(c->desc.collision, p2p, &ctas, &c->pg_threads[p2p ? 1 : 0]);
+        else c->ops->persist_grid32(c->desc.collision, p2p, &ctas, &c->pg_threads[p2p ? 1 : 0]);
+    }
+    return ctas > 0;
+}
+
+// m fused steps from post-collision populations in buf[cur], one launch
+template <typename T>
+static int do_persist(lbm_ctx *c, long long t0, long long m) {
+    const bool p2p = c->desc.world > 1;
+    const int ctas = c->pg_ctas[p2p ? 1 : 0], threads = c->pg_threads[p2p ? 1 : 0];
+    int rc = wait_comm(c);
+    if (rc) return rc;
+    if (c->pdone_ctas < ctas) {
+        if (c->pdone) { CU(cudaStreamSynchronize(c->stream)); cudaFree(c->pdone); c->pdone = nullptr; }
+        CU(cudaMalloc(&c->pdone, (size_t)(ctas + 4) * sizeof(unsigned long long)));
+        CU(cudaMemsetAsync(c->pdone, 0, (size_t)(ctas + 4) * sizeof(unsigned long long), c->stream));
+        c->pdone_ctas = ctas;
+    }
+    CU(cudaMemsetAsync(c->pdone + 1, 0, (size_t)(ctas + 3) * sizeof(unsigned long long), c->stream));  // all but the sticky error word
+    const long long N = (long long)c->desc.nx * c->nyl, H = c->li.H;
+    PersistArgs a;
+    memset(&a, 0, sizeof(a));
+    a.nsteps = (int)m;
+    a.step0 = t0;
+    a.error = c->pdone; a.edge_count = c->pdone + 1; a.done = c->pdone + 4;
+    a.epoch0 = c->epoch;
+    a.npc = (N + ctas - 1) / ctas;
+    a.nctas = (int)((N + a.npc - 1) / a.npc);
+    a.n_bot = (int)((H * c->desc.nx - 1) / a.npc) + 1;
+    a.n_top = a.nctas - (int)(((long long)(c->nyl - H) * c->desc.nx) / a.npc);
+    KParams<T> pa = make_params<T>(c, c->cur, 1 - c->cur), pb = make_params<T>(c, 1 - c->cur, c->cur);
+    if (p2p) {
+        fill_p2p<T>(c, pa, 1 - c->cur);
+        fill_p2p<T>(c, pb, c->cur);
+        c->epoch += (unsigned long long)m;
+        c->p2p_in_batch = true;
+    }
+    int lrc;
+    if (std::is_same<T, double>::value)
+        lrc = c->ops->persist64(c->desc.collision, p2p, reinterpret_cast<const KParams<double> &>(pa), reinterpret_cast<const KParams<double> &>(pb), a, ctas, threads, c->stream);
+    else
+        lrc = c->ops->persist32(c->desc.collision, p2p, reinterpret_cast<const KParams<float> &>(pa), reinterpret_cast<const KParams<float> &>(pb), a, ctas, threads, c->stream);
+    if (lrc != 0) return fail(LBM_ERR_CUDA, "cooperative launch of the persistent step kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+    c->launches += 1;
+    c->persist_used = true;
+    if (m & 1) c->cur = 1 - c->cur;
+    return 0;
+}
+
 template <typename T>
 static int do_steps(lbm_ctx *c, long long t0, long long n) {
     for (long long k = 0; k < n; ++k) {
         const long long t = t0 + k;
         int rc;
+        if (c->state == ST_COLLIDED && n - k <= 0x7fffffffLL && persist_ok(c, n - k)) {
+            rc = do_persist<T>(c, t, n - k);
+            if (rc) return rc;
+            break;
+        }
         if (c->state == ST_COLLIDED && !c->comm_pending && n - k >= GRAPH_STEPS && graph_ok(c)) {
             const int src = c->cur;
             if (!c->graph[src] && build_graph<T>(c, src) != 0) {
@@ -708,7 +808,7 @@ void lbm_destroy(lbm_ctx *c) {
     p2p_unmap(c);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     if (c->arena) { cudaFree(c->arena); c->buf[0] = c->buf[1] = nullptr; }
-    for (void *p : {c->buf[0], c->buf[1], c->field, c->sep_fx, c->sep_fy, (void *)c->partials, (void *)c->red_out, (void *)c->u_old, (void *)c->rho_old, (void *)c->stage})
+    for (void *p : {c->buf[0], c->buf[1], c->field, c->sep_fx, c->sep_fy, (void *)c->partials, (void *)c->red_out, (void *)c->u_old, (void *)c->rho_old, (void *)c->stage, (void *)c->err_dev, (void *)c->pdone})
         if (p) cudaFree(p);
     for (cudaEvent_t e : {c->ev_b, c->ev_c, c->ev_t0, c->ev_t1, c->ev_u0, c->ev_u1, c->ev_fork})
         if (e) cudaEventDestroy(e);
@@ -1192,7 +1292,7 @@ int lbm_step(lbm_ctx *c, int64_t t0, int64_t nsteps, double dt) {
     CU(cudaSetDevice(c->desc.device));
     int rc = check_force_window(c, t0, nsteps);
     if (rc) return rc;
-    if (c->p2p_failed) return p2p_check(c);
+    if (c->p2p_failed || c->persist_failed) return p2p_check(c);
     CU(cudaEventRecord(c->ev_t0, c->stream));
     c->p2p_in_batch = false;
     if (c->p2p_on && c->opt_p2p) {
@@ -1269,6 +1369,7 @@ int lbm_set_option(lbm_ctx *c, const char *key, int64_t value) {
     else if (!strcmp(key, "graph")) c->opt_graph = (int)value;
     else if (!strcmp(key, "overlap")) c->opt_overlap = (int)value;
     else if (!strcmp(key, "p2p")) c->opt_p2p = (int)value;
+    else if (!strcmp(key, "persistent")) c->opt_persistent = (int)value;
     else return fail(LBM_ERR_INVALID, "unknown option '%s'", key);
     return 0;
 }
@@ -1323,9 +1424,14 @@ int lbm_reduce_errors(lbm_ctx *c, double tau_visc, double u_max, const lbm_sep_f
             if (expected[f].y[k]) memcpy(t + nx, expected[f].y[k], (size_t)nyl * 8);
         }
     }
-    double *dev = nullptr;
     const int nblocks = 1024;
-    CU(cudaMalloc(&dev, (tab.size() + (size_t)nblocks * 16 + 16) * 8));
+    const size_t need = tab.size() + (size_t)nblocks * 16 + 16;
+    if (c->err_doubles < need) {
+        if (c->err_dev) { CU(cudaStreamSynchronize(c->stream)); cudaFree(c->err_dev); c->err_dev = nullptr; c->err_doubles = 0; }
+        CU(cudaMalloc(&c->err_dev, need * 8));
+        c->err_doubles = need;
+    }
+    double *dev = c->err_dev;
     cudaError_t e = cudaMemcpyAsync(dev, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, c->stream);
     ea.tab = dev;
     ea.partials = dev + tab.size();
@@ -1343,7 +1449,6 @@ int lbm_reduce_errors(lbm_ctx *c, double tau_visc, double u_max, const lbm_sep_f
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(h, ea.out, sizeof(h), cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    cudaFree(dev);
     if (e != cudaSuccess) return fail(LBM_ERR_CUDA, "lbm_reduce_errors: %s", cudaGetErrorString(e));
     memcpy(out, h, sizeof(h));
     return p2p_check(c);

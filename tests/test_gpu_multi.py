@@ -9,7 +9,8 @@ import pytest
 pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
 
 
-def _worker(rank, world, idq, out, lattice, model, nx, ny, nsteps, walls, dtype, overlap, p2p=1, single_steps=False, arith=0):
+def _worker(rank, world, idq, out, lattice, model, nx, ny, nsteps, walls, dtype, overlap, p2p=1, single_steps=False, arith=0,
+            persistent=2):
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, root)
@@ -38,6 +39,7 @@ def _worker(rank, world, idq, out, lattice, model, nx, ny, nsteps, walls, dtype,
         c = _abi.Context(nx, ny, lattice, code, taus, bcs, dtype=dtype, arith=arith, device=rank, rank=rank, world=world, nccl_id=nid)
         c.set_option("overlap", overlap)
         c.set_option("p2p", 1 if p2p else 0)
+        c.set_option("persistent", persistent)  # 0: plain launches / graphs, 1: persistent kernel wherever possible, 2: automatic
         path = c.halo_path
         assert (c.y0, c.ny_local) == lbm.slab_rows(ny, rank, world)
         c.set_force_uniform(1e-6, 2e-6)
@@ -64,7 +66,7 @@ def _gpus():
     return torch.cuda.device_count()
 
 
-def _run_slabs(lattice, model, walls, overlap, p2p, world=2, nx=40, ny=37, nsteps=9, single_steps=False):
+def _run_slabs(lattice, model, walls, overlap, p2p, world=2, nx=40, ny=37, nsteps=9, single_steps=False, persistent=2):
     import torch.multiprocessing as mp
     import oracle.lbm_oracle as O
     qo = O.L.BY_NAME[lattice]()
@@ -82,7 +84,7 @@ def _run_slabs(lattice, model, walls, overlap, p2p, world=2, nx=40, ny=37, nstep
     ctx = mp.get_context("spawn")
     idq, out = ctx.Queue(), ctx.Queue()
     procs = [ctx.Process(target=_worker, args=(r, world, idq, out, lattice, model, nx, ny, nsteps, walls, 0, overlap, p2p,
-                                               single_steps))
+                                               single_steps, 0, persistent))
              for r in range(world)]
     for p in procs:
         p.start()
@@ -115,8 +117,13 @@ def _run_slabs(lattice, model, walls, overlap, p2p, world=2, nx=40, ny=37, nstep
     # NCCL send/recv path (LBM_P2P=0 / boxes without peer access)
     ("D2Q9", "TRT", True, 1, 0), ("D2Q9", "SRT", True, 0, 0), ("D2Q37", "TRT", True, 1, 0),
 ])
-def test_two_slabs_equal_single_domain(lattice, model, walls, overlap, p2p):
-    _run_slabs(lattice, model, walls, overlap, p2p)
+@pytest.mark.parametrize("persistent", [0, 1])
+def test_two_slabs_equal_single_domain(lattice, model, walls, overlap, p2p, persistent):
+    """persistent = 0: boundary-row + interior launches per step (CUDA graphs for long batches); 1: the persistent
+    multi-step kernel whose edge CTAs push the boundary rows and hand-shake with the neighbours mid-step."""
+    if persistent and not p2p:
+        pytest.skip("the persistent kernel exchanges halos through peer memory only")
+    _run_slabs(lattice, model, walls, overlap, p2p, persistent=persistent)
 
 
 def _peer_access(a=0, b=1):
@@ -138,8 +145,21 @@ def test_peer_memory_path_is_taken_on_nvlink_boxes():
     ("D2Q37", "TRT", True, 515, 47, 24, False),     # halo 3, odd width
     ("D2Q21", "TRT", False, 64, 13, 12, True),      # thin slabs (6/7 rows <= 2H+1 on one rank): single-launch path
 ])
-def test_peer_memory_stress(lattice, model, walls, nx, ny, nsteps, single_steps):
-    _run_slabs(lattice, model, walls, 1, 1, nx=nx, ny=ny, nsteps=nsteps, single_steps=single_steps)
+@pytest.mark.parametrize("persistent", [0, 1])
+def test_peer_memory_stress(lattice, model, walls, nx, ny, nsteps, single_steps, persistent):
+    _run_slabs(lattice, model, walls, 1, 1, nx=nx, ny=ny, nsteps=nsteps, single_steps=single_steps, persistent=persistent)
+
+
+@pytest.mark.parametrize("lattice,model,walls,nx,ny,nsteps", [
+    ("D2Q9", "TRT", False, 1024, 2048, 40),    # 1024 x 1024 per GPU: the launch-bound case the persistent kernel is for
+    ("D2Q9", "SRT", True, 1024, 512, 101),     # C3-like channel, odd step count
+    ("D2Q37", "TRT", True, 2048, 64, 21),      # halo 3: the boundary rows of an edge span several CTAs
+    ("D2Q17", "MRT", False, 256, 300, 33),
+])
+def test_persistent_kernel_slabs_at_production_sizes(lattice, model, walls, nx, ny, nsteps):
+    """The persistent multi-step kernel across two GPUs at sizes where every SM holds several CTAs of the cooperative
+    grid: bit-identical (SRT/TRT) to the single-domain oracle."""
+    _run_slabs(lattice, model, walls, 1, 1, nx=nx, ny=ny, nsteps=nsteps, persistent=1)
 
 
 @pytest.mark.parametrize("world", [3, 4, 8])

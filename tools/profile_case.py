@@ -32,6 +32,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--walls", action="store_true")
+    ap.add_argument("--persistent", type=int, default=2, help="0: launch per step / graphs, 1: persistent kernel, 2: automatic")
+    ap.add_argument("--graph", type=int, default=1)
     ap.add_argument("--diag", action="store_true", help="time lbm_moments / lbm_reduce / lbm_reduce_errors instead")
     ap.add_argument("--sustain", type=float, default=0.0, help="repeat the timed batch for at least this many seconds")
     a = ap.parse_args()
@@ -57,10 +59,13 @@ def main():
     with _abi.Context(n, ny, a.lattice, code, taus, bcs, dtype=_abi.F64 if a.dtype == "f64" else _abi.F32,
                       arith=_abi.ARITH_FAST if a.arith == "fast" else _abi.ARITH_EXACT) as c:
         c.set_option("variant", a.variant)
+        c.set_option("persistent", a.persistent)
+        c.set_option("graph", a.graph)
         c.upload_f(f0)
         c.step(0, 4)
         c.sync()
-        out = dict(lattice=a.lattice, model=a.model, dtype=a.dtype, arith=a.arith, variant=a.variant, n=n, ny=ny)
+        out = dict(lattice=a.lattice, model=a.model, dtype=a.dtype, arith=a.arith, variant=a.variant, n=n, ny=ny,
+                   persistent=a.persistent, graph=a.graph)
         if a.diag:
             import time
             one = np.ones(n)
@@ -84,9 +89,11 @@ def main():
             t_end = time.perf_counter() + a.sustain
             tot_ms, tot_steps = 0.0, 0
             while True:
+                l0 = c.kernel_launches
                 c.timer_start()
                 c.step(0, a.steps)
                 tot_ms += c.timer_stop()
+                out["launches_per_batch"] = c.kernel_launches - l0
                 tot_steps += a.steps
                 if time.perf_counter() >= t_end:
                     break
