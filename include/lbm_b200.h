@@ -203,6 +203,24 @@ typedef struct {
 } lbm_sep_field;
 int lbm_reduce_errors(lbm_ctx *ctx, double tau_visc, double u_max, const lbm_sep_field expected[8], double out[16]);
 
+/* initialize(strategy, q, problem) (src/initial_conditions.jl:7-22) evaluated entirely on the device for the local slab:
+ *   f_stream := hermite_based_equilibrium!(q, rho, u, T) [+ offeq_coef w_i [rho] dot(hermite(Val{2}, c_i, q), grad u + (grad u)')]
+ * with the problem's analytic fields in the separable form of lbm_sep_field (x tables: nx entries, y tables: ny_local):
+ *   rho, ux, uy, p : lattice_density / lattice_velocity / pressure (problems/problems.jl:97-106); T = p / rho as in
+ *                    equilibrium(q, problem, x, y) (problems.jl:121-128) unless unit_temperature; rho := 1 if unit_density
+ *                    (ConstantDensity, constant_density.jl:10-20; AnalyticalVelocityAndStress, analytical_velocity_stress.jl:5-31)
+ *   grad[4]        : du_x/dx, du_x/dy, du_y/dx, du_y/dy for the off-equilibrium strategies
+ *                    (analytical_offequilibrium.jl:10-87: offeq = 1 generic, offeq = 2 the TGV method with the factor rho)
+ * The host moves O(nx + ny) numbers instead of Q (or 4) per node. */
+typedef struct {
+    lbm_sep_field rho, ux, uy, p;
+    lbm_sep_field grad[4];
+    int32_t unit_density, unit_temperature;
+    int32_t offeq; /* 0: equilibrium only; 1: + offeq_coef w_i dot(H2_i, S); 2: + offeq_coef w_i rho dot(H2_i, S), S = grad + grad' */
+    double offeq_coef;
+} lbm_init_spec;
+int lbm_init_analytic(lbm_ctx *ctx, const lbm_init_spec *spec);
+
 /* Introspection used by bench.py / tests. */
 int64_t lbm_kernel_launches(const lbm_ctx *ctx); /* kernels launched by this context so far */
 /* How halos travel between y-slabs: 0 = single GPU (ghost cells written by the kernels themselves), 1 = NCCL

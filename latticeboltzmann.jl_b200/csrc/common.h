@@ -167,6 +167,17 @@ struct PersistArgs {
     int n_bot, n_top;              // CTAs owning nodes of the bottom / top H rows
 };
 
+// Device-side initialize(): analytic fields in separable form (same layout as ErrorArgs): rho, ux, uy, p (lattice units),
+// du_x/dx, du_x/dy, du_y/dx, du_y/dy.
+struct InitArgs {
+    double c0[8];
+    double a[8][2];
+    const double *tab;   // [8][2][nx + nyl]
+    int unit_density, unit_temperature;
+    int offeq;           // 0: equilibrium only, 1: + coef w_i dot(H2_i, grad + grad'), 2: the same times rho
+    double coef;
+};
+
 // Launchers exported by one kernels_inst.cu instance.
 struct Ops {
     int lattice, arith;
@@ -200,6 +211,8 @@ struct Ops {
     // device-side hermite_based_equilibrium! from host-provided (rho, ux, uy, T) rows
     void (*init_eq64)(const KParams<double> &p, const double *rho, const double *ux, const double *uy, const double *T, cudaStream_t s);
     void (*init_eq32)(const KParams<float> &p, const double *rho, const double *ux, const double *uy, const double *T, cudaStream_t s);
+    void (*init_analytic64)(const KParams<double> &p, const InitArgs &ia, cudaStream_t s);
+    void (*init_analytic32)(const KParams<float> &p, const InitArgs &ia, cudaStream_t s);
     // persistent multi-step kernel: co-resident grid (CTAs, threads) for this <collision model, dtype>, 0 CTAs if the
     // device cannot launch cooperatively; pa: src = current state, pb: the two buffers swapped
     void (*persist_grid64)(int cm, bool p2p, int *ctas, int *threads);

@@ -919,55 +919,94 @@ __global__ void __launch_bounds__(128) k_reduce_final(const ReduceArgs ra) { fin
 //   f_i = w_i (rho + sum_{n=1..N} <a_eq^(n), H_n(c_i)> / (n! (1/css)^n)),  a_eq = equilibrium_coefficient(Val{n}, q, rho, u, T)
 // including the (T - 1) terms and the Val{4} delta-index quirk (hermite.jl:69,71), evaluated over the full
 // (non-symmetric) index set.  Writes rows [0, p.nyl) of dst (the caller offsets dst / sets nyl).
+// one node: f_i (or f_i - w_i for Float32 storage) + extra_i -> dst
+template <typename T, class Extra>
+__device__ __forceinline__ void init_eq_node(const KParams<T> &p, int x, int y, double rho, double u0, double u1, double Tm1, Extra &&extra) {
+    const LatConst<double> &c = c_lat64;
+    const double u[2] = {u0, u1};
+    const double cs = c.cs_inv;
+    // a_eq^(n)[t], t = bit string of the indices (bit k = k-th index)
+    double a2[4], a3[8], a4[16];
+    auto d = [](int a, int b) { return a == b ? 1.0 : 0.0; };
+    for (int t = 0; t < 4; ++t) {
+        const int a = t & 1, b = (t >> 1) & 1;
+        a2[t] = rho * (u[a] * u[b] + cs * Tm1 * d(a, b));
+    }
+    for (int t = 0; t < 8; ++t) {
+        const int a = t & 1, b = (t >> 1) & 1, e = (t >> 2) & 1;
+        a3[t] = rho * (u[a] * u[b] * u[e] + cs * Tm1 * (u[a] * d(b, e) + u[b] * d(a, e) + u[e] * d(a, b)));
+    }
+    for (int t = 0; t < 16; ++t) {
+        const int a = t & 1, b = (t >> 1) & 1, e = (t >> 2) & 1, g = (t >> 3) & 1;
+        a4[t] = rho * (u[a] * u[b] * u[e] * u[g]
+                       + cs * Tm1 * (u[a] * u[b] * d(e, g) + u[a] * u[e] * d(b, g) + u[a] * u[g] * d(b, g)
+                                     + u[b] * u[e] * d(a, g) + u[b] * u[g] * d(a, g) + u[e] * u[g] * d(a, b))
+                       + cs * cs * Tm1 * Tm1 * (d(a, b) * d(e, g) + d(a, e) * d(b, g) + d(a, g) * d(b, e)));
+    }
+    static_for<0, Q>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        double s = (rho * u[0] * L::cx(i) + rho * u[1] * L::cy(i)) / cs;
+        if constexpr (NH >= 2) {
+            double dot = 0;
+            for (int t = 0; t < 4; ++t) dot += a2[t] * c.H2[i][__popc(t)];
+            s += dot / (2 * cs * cs);
+        }
+        if constexpr (NH >= 3) {
+            double dot = 0;
+            for (int t = 0; t < 8; ++t) dot += a3[t] * c.H3[i][__popc(t)];
+            s += dot / (6 * cs * cs * cs);
+        }
+        if constexpr (NH >= 4) {
+            double dot = 0;
+            for (int t = 0; t < 16; ++t) dot += a4[t] * c.H4[i][__popc(t)];
+            s += dot / (24 * cs * cs * cs * cs);
+        }
+        const long long m = i * p.plane + (long long)y * p.pitch + x;
+        const double ex = extra(I);
+        if constexpr (Shifted<T>::value) p.dst[m] = (T)(c.w[i] * ((rho - 1) + s) + ex);
+        else p.dst[m] = (T)(c.w[i] * (rho + s) + ex);
+    });
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) k_init_eq(const __grid_constant__ KParams<T> p, const double *rho_, const double *ux_,
                                                  const double *uy_, const double *T_) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= p.nx) return;
-    const LatConst<double> &c = c_lat64;
     for (int y = blockIdx.y * blockDim.y + threadIdx.y; y < p.nyl; y += gridDim.y * blockDim.y) {
         const long long n = (long long)y * p.nx + x;
-        const double rho = rho_[n], u[2] = {ux_[n], uy_[n]}, Tm1 = T_[n] - 1;
-        const double cs = c.cs_inv;
-        // a_eq^(n)[t], t = bit string of the indices (bit k = k-th index)
-        double a2[4], a3[8], a4[16];
-        auto d = [](int a, int b) { return a == b ? 1.0 : 0.0; };
-        for (int t = 0; t < 4; ++t) {
-            const int a = t & 1, b = (t >> 1) & 1;
-            a2[t] = rho * (u[a] * u[b] + cs * Tm1 * d(a, b));
+        init_eq_node<T>(p, x, y, rho_[n], ux_[n], uy_[n], T_[n] - 1, [](auto) { return 0.0; });
+    }
+}
+
+// K7b: initialize(strategy, q, problem) entirely on the device.  The problem's analytic fields arrive in separable form
+// (sums of <= 2 products X(x) Y(y), as for the error norms): lattice density, velocity, pressure (T = p / rho,
+// problems.jl:97-106, 121-128) and the velocity gradient for the strategies that add the off-equilibrium part
+//   f_i += coef w_i [rho] dot(hermite(Val{2}, c_i, q), grad u + (grad u)')
+// (analytical_offequilibrium.jl:10-87, analytical_velocity_stress.jl:5-31).  The host moves O(NX + NY) numbers.
+template <typename T>
+__global__ void __launch_bounds__(256) k_init_analytic(const __grid_constant__ KParams<T> p, const __grid_constant__ InitArgs ia) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= p.nx) return;
+    const int W = p.nx + p.nyl;
+    const LatConst<double> &c = c_lat64;
+    for (int y = blockIdx.y * blockDim.y + threadIdx.y; y < p.nyl; y += gridDim.y * blockDim.y) {
+        double e[8];
+#pragma unroll
+        for (int f = 0; f < 8; ++f) {
+            const double *t0 = ia.tab + (size_t)(2 * f) * W, *t1 = t0 + W;
+            e[f] = ia.c0[f] + ia.a[f][0] * (__ldg(t0 + x) * __ldg(t0 + p.nx + y)) + ia.a[f][1] * (__ldg(t1 + x) * __ldg(t1 + p.nx + y));
         }
-        for (int t = 0; t < 8; ++t) {
-            const int a = t & 1, b = (t >> 1) & 1, e = (t >> 2) & 1;
-            a3[t] = rho * (u[a] * u[b] * u[e] + cs * Tm1 * (u[a] * d(b, e) + u[b] * d(a, e) + u[e] * d(a, b)));
-        }
-        for (int t = 0; t < 16; ++t) {
-            const int a = t & 1, b = (t >> 1) & 1, e = (t >> 2) & 1, g = (t >> 3) & 1;
-            a4[t] = rho * (u[a] * u[b] * u[e] * u[g]
-                           + cs * Tm1 * (u[a] * u[b] * d(e, g) + u[a] * u[e] * d(b, g) + u[a] * u[g] * d(b, g)
-                                         + u[b] * u[e] * d(a, g) + u[b] * u[g] * d(a, g) + u[e] * u[g] * d(a, b))
-                           + cs * cs * Tm1 * Tm1 * (d(a, b) * d(e, g) + d(a, e) * d(b, g) + d(a, g) * d(b, e)));
-        }
-        static_for<0, Q>([&](auto I) {
+        const double rho = ia.unit_density ? 1.0 : e[0];
+        const double Tm1 = ia.unit_temperature ? 0.0 : e[3] / e[0] - 1;
+        const double sxx = e[4] + e[4], sxy = e[5] + e[6], syy = e[7] + e[7];
+        const double kk = ia.offeq == 0 ? 0.0 : (ia.offeq == 2 ? ia.coef * rho : ia.coef);
+        init_eq_node<T>(p, x, y, rho, e[1], e[2], Tm1, [&](auto I) {
             constexpr int i = decltype(I)::value;
-            double s = (rho * u[0] * L::cx(i) + rho * u[1] * L::cy(i)) / cs;
-            if constexpr (NH >= 2) {
-                double dot = 0;
-                for (int t = 0; t < 4; ++t) dot += a2[t] * c.H2[i][__popc(t)];
-                s += dot / (2 * cs * cs);
-            }
-            if constexpr (NH >= 3) {
-                double dot = 0;
-                for (int t = 0; t < 8; ++t) dot += a3[t] * c.H3[i][__popc(t)];
-                s += dot / (6 * cs * cs * cs);
-            }
-            if constexpr (NH >= 4) {
-                double dot = 0;
-                for (int t = 0; t < 16; ++t) dot += a4[t] * c.H4[i][__popc(t)];
-                s += dot / (24 * cs * cs * cs * cs);
-            }
-            const long long m = i * p.plane + (long long)y * p.pitch + x;
-            if constexpr (Shifted<T>::value) p.dst[m] = (T)(c.w[i] * ((rho - 1) + s));
-            else p.dst[m] = (T)(c.w[i] * (rho + s));
+            if (ia.offeq == 0) return 0.0;
+            // dot over the full 2 x 2 index set: H11 S11 + H12 S12 + H21 S21 + H22 S22
+            const double dot = ((c.H2[i][0] * sxx + c.H2[i][1] * sxy) + c.H2[i][1] * sxy) + c.H2[i][2] * syy;
+            return (c.w[i] * kk) * dot;
         });
     }
 }
@@ -1179,6 +1218,12 @@ static void launch_init_eq(const KParams<T> &p, const double *rho, const double 
     k_init_eq<T><<<grid_for(p, block, p.nyl, p.nx), block, 0, s>>>(p, rho, ux, uy, Tm);
 }
 
+template <typename T>
+static void launch_init_analytic(const KParams<T> &p, const InitArgs &ia, cudaStream_t s) {
+    dim3 block; pick_block(p.nx, block);
+    k_init_analytic<T><<<grid_for(p, block, p.nyl, p.nx), block, 0, s>>>(p, ia);
+}
+
 #include "batch.cuh"
 #include "persist.cuh"
 
@@ -1195,6 +1240,7 @@ static const Ops ops = {
     &launch_errors<double>, &launch_errors<float>,
     &launch_import32, &launch_export32,
     &launch_init_eq<double>, &launch_init_eq<float>,
+    &launch_init_analytic<double>, &launch_init_analytic<float>,
     &persist_grid<double>, &persist_grid<float>,
     &launch_persist<double>, &launch_persist<float>,
     &launch_batch<double>, &launch_batch<float>,

@@ -1122,6 +1122,49 @@ int lbm_init_equilibrium_rows(lbm_ctx *c, int32_t y0, int32_t ny, const double *
     return 0;
 }
 
+int lbm_init_analytic(lbm_ctx *c, const lbm_init_spec *spec) {
+    if (!c || !spec) return fail(LBM_ERR_INVALID, "null argument");
+    if (spec->offeq < 0 || spec->offeq > 2) return fail(LBM_ERR_INVALID, "offeq %d", spec->offeq);
+    CU(cudaSetDevice(c->desc.device));
+    int rc = materialize(c);
+    if (rc) return rc;
+    rc = wait_comm(c);
+    if (rc) return rc;
+    const int nx = c->desc.nx, nyl = c->nyl, W = nx + nyl;
+    std::vector<double> tab((size_t)16 * W, 1.0);
+    InitArgs ia;
+    memset(&ia, 0, sizeof(ia));
+    const lbm_sep_field *fields[8] = {&spec->rho, &spec->ux, &spec->uy, &spec->p, &spec->grad[0], &spec->grad[1], &spec->grad[2], &spec->grad[3]};
+    for (int f = 0; f < 8; ++f) {
+        ia.c0[f] = fields[f]->c0;
+        for (int k = 0; k < 2; ++k) {
+            ia.a[f][k] = fields[f]->a[k];
+            double *t = tab.data() + (size_t)(2 * f + k) * W;
+            if (fields[f]->x[k]) memcpy(t, fields[f]->x[k], (size_t)nx * 8);
+            if (fields[f]->y[k]) memcpy(t + nx, fields[f]->y[k], (size_t)nyl * 8);
+        }
+    }
+    ia.unit_density = spec->unit_density; ia.unit_temperature = spec->unit_temperature;
+    ia.offeq = spec->offeq; ia.coef = spec->offeq_coef;
+    double *dev = nullptr;
+    CU(cudaMalloc(&dev, tab.size() * 8));
+    cudaError_t e = cudaMemcpyAsync(dev, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, c->stream);
+    ia.tab = dev;
+    if (e == cudaSuccess) {
+        if (is64(c)) c->ops->init_analytic64(make_params<double>(c, c->cur, c->cur), ia, c->stream);
+        else c->ops->init_analytic32(make_params<float>(c, c->cur, c->cur), ia, c->stream);
+        c->launches += 1;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(dev);
+    if (e != cudaSuccess) return fail(LBM_ERR_CUDA, "lbm_init_analytic: %s", cudaGetErrorString(e));
+    c->state = ST_STREAM;
+    c->have_coll = false;
+    c->resume_ok = false;
+    return 0;
+}
+
 int lbm_download_f_rows(lbm_ctx *c, int32_t y0, int32_t ny, double *f_rows) {
     if (!c || !f_rows) return fail(LBM_ERR_INVALID, "null argument");
     CU(cudaSetDevice(c->desc.device));

@@ -38,6 +38,7 @@ EXPORTS = [
     "lbm_collide", "lbm_stream", "lbm_apply_bcs", "lbm_step", "lbm_sync", "lbm_moments", "lbm_reduce",
     "lbm_reduce_errors",
     "lbm_kernel_launches", "lbm_halo_path", "lbm_last_step_ms", "lbm_timer_start", "lbm_timer_stop", "lbm_set_option",
+    "lbm_init_analytic",
     "lbm_batch_create", "lbm_batch_destroy", "lbm_batch_set_tau", "lbm_batch_set_force_uniform", "lbm_batch_upload_f",
     "lbm_batch_broadcast_f", "lbm_batch_download_f", "lbm_batch_run", "lbm_batch_status", "lbm_batch_reduce_errors",
     "lbm_batch_last_run_ms", "lbm_batch_kernel_launches",
@@ -59,6 +60,12 @@ class lbm_bc(C.Structure):
 
 class lbm_sep_field(C.Structure):
     _fields_ = [("c0", C.c_double), ("a", C.c_double * 2), ("x", C.c_void_p * 2), ("y", C.c_void_p * 2)]
+
+
+class lbm_init_spec(C.Structure):
+    _fields_ = [("rho", lbm_sep_field), ("ux", lbm_sep_field), ("uy", lbm_sep_field), ("p", lbm_sep_field),
+                ("grad", lbm_sep_field * 4), ("unit_density", C.c_int32), ("unit_temperature", C.c_int32),
+                ("offeq", C.c_int32), ("offeq_coef", C.c_double)]
 
 
 class lbm_batch_stop(C.Structure):
@@ -126,6 +133,7 @@ def lib():
     l.lbm_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     l.lbm_timer_start.argtypes = [vp]
     l.lbm_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
+    l.lbm_init_analytic.argtypes = [vp, C.POINTER(lbm_init_spec)]
     l.lbm_batch_create.argtypes = [C.POINTER(lbm_desc), C.c_int32, C.POINTER(vp)]
     l.lbm_batch_destroy.argtypes = [vp]
     l.lbm_batch_destroy.restype = None
@@ -273,6 +281,20 @@ class Context:
         ny = np.shape(rho)[1]
         arrs = [np.asfortranarray(np.broadcast_to(np.asarray(a, dtype=np.float64), (self.nx, ny))) for a in (rho, ux, uy, T)]
         check(lib().lbm_init_equilibrium_rows(self._h, int(y0), int(ny), *[a.ctypes.data for a in arrs]))
+
+    def init_analytic(self, fields, unit_density=False, unit_temperature=False, offeq=0, offeq_coef=0.0):
+        """f_stream := equilibrium (+ off-equilibrium part) of the analytic fields, evaluated on the device.  fields: 8
+        separable fields (c0, [(a, X or None, Y or None), ...]) for rho, ux, uy, p, du_x/dx, du_x/dy, du_y/dx, du_y/dy
+        (lattice units; X: NX entries, Y: NY_local entries)."""
+        arr, keep = _sep_fields(fields, self.nx, self.ny_local)
+        spec = lbm_init_spec()
+        spec.rho, spec.ux, spec.uy, spec.p = arr[0], arr[1], arr[2], arr[3]
+        for k in range(4):
+            spec.grad[k] = arr[4 + k]
+        spec.unit_density, spec.unit_temperature = int(bool(unit_density)), int(bool(unit_temperature))
+        spec.offeq, spec.offeq_coef = int(offeq), float(offeq_coef)
+        check(lib().lbm_init_analytic(self._h, C.byref(spec)))
+        del keep
 
     def download_f_rows(self, y0, ny):
         out = np.empty((self.nx, int(ny), self.Q), dtype=np.float64, order="F")

@@ -127,10 +127,68 @@ def initialize(strategy, q, problem, cm=None, rows=None):
     return np.asfortranarray(f, dtype=np.float64)
 
 
-def initialize_on_device(strategy, q, problem, ctx, chunk_nodes=1 << 24):
-    """initialize(strategy, q, problem) evaluated on the device: the host only produces the analytic
-    (rho, u, T) fields, row block by row block; the Hermite-series equilibrium runs in the CUDA library
-    (lbm_init_equilibrium_rows).  Supports the equilibrium-only strategies; returns False otherwise."""
+def analytic_init_spec(strategy, q, problem, y0=0, ny=None):
+    """The arguments of Context.init_analytic for `strategy`: the problem's fields in separable form, found from
+    O(NX + NY) evaluations of its pointwise functions (separable.decompose_function), plus the off-equilibrium
+    coefficient of the strategy.  None when the strategy has no closed form or some field is not of rank <= 2."""
+    from .separable import decompose_function
+    xs, ys = problem._xy(y0, ny)
+    cs = q.speed_of_sound_squared
+    zero = (0.0, [])
+    kw = dict(unit_density=False, unit_temperature=False, offeq=0, offeq_coef=0.0)
+    grad_scale = None
+    if isinstance(strategy, ZeroVelocityInitialCondition):
+        return [(1.0, []), zero, zero, (1.0, [])] + [zero] * 4, dict(kw, unit_density=True, unit_temperature=True)
+    if isinstance(strategy, AnalyticalEquilibrium):
+        pass
+    elif isinstance(strategy, ConstantDensity):
+        kw.update(unit_density=True, unit_temperature=True)
+    elif isinstance(strategy, AnalyticalVelocityAndStress):  # analytical_velocity_stress.jl:5-31
+        tau_eff = cs * problem.lattice_viscosity() + 0.5
+        kw.update(unit_density=True, unit_temperature=True, offeq=1, offeq_coef=-(cs * tau_eff * 1.0 * 1.0) / 2)
+        grad_scale = problem.u_max ** 2
+    elif isinstance(strategy, AnalyticalEquilibriumAndOffEquilibrium):  # analytical_offequilibrium.jl:10-87
+        tau = cs * problem.lattice_viscosity()
+        if isinstance(problem, TGV):
+            kw.update(offeq=2, offeq_coef=-(cs * (tau + 0.5) * 1.0) / 2)
+            grad_scale = 1.0
+        else:
+            factor = problem.domain_size[0] * problem.domain_size[1]
+            kw.update(offeq=1, offeq_coef=-factor * 0.5 * ((tau + 0.5) * cs))
+            grad_scale = problem.u_max ** 2
+    else:
+        return None
+    fns = [lambda X, Y: problem.lattice_density(q, X, Y),
+           lambda X, Y: problem.lattice_velocity(q, X, Y)[0],
+           lambda X, Y: problem.lattice_velocity(q, X, Y)[1],
+           lambda X, Y: problem.pressure(q, X, Y)]
+    if kw["unit_density"] and kw["unit_temperature"]:
+        fns[0] = fns[3] = None
+    if grad_scale is not None:
+        for a, b in ((0, 0), (0, 1), (1, 0), (1, 1)):  # du_x/dx, du_x/dy, du_y/dx, du_y/dy
+            fns.append(lambda X, Y, a=a, b=b: grad_scale * np.asarray(problem.velocity_gradient(X, Y, 0.0)[a][b]))
+    else:
+        fns += [None] * 4
+    fields = []
+    for fn in fns:
+        sep = (1.0, []) if fn is None and len(fields) in (0, 3) else zero if fn is None else decompose_function(fn, xs, ys)
+        if sep is None:
+            return None
+        fields.append(sep)
+    return fields, kw
+
+
+def initialize_on_device(strategy, q, problem, ctx, chunk_nodes=1 << 24, analytic=True):
+    """initialize(strategy, q, problem) evaluated on the device.  Every closed-form strategy (equilibrium, constant
+    density, velocity + stress, equilibrium + off-equilibrium, zero velocity) goes through lbm_init_analytic: the host
+    passes the problem's rho, u, p and grad u as separable tables (O(NX + NY) numbers) and the kernel evaluates the
+    Hermite-series equilibrium and the off-equilibrium part per node.  Problems whose fields are not of rank <= 2 fall
+    back, for the equilibrium-only strategies, to (rho, u, T) row blocks from the host (lbm_init_equilibrium_rows).
+    Returns False when the strategy cannot be evaluated on the device."""
+    spec = analytic_init_spec(strategy, q, problem, ctx.y0, ctx.ny_local) if analytic else None
+    if spec is not None:
+        ctx.init_analytic(spec[0], **spec[1])
+        return True
     if not isinstance(strategy, (ZeroVelocityInitialCondition, AnalyticalEquilibrium, ConstantDensity)):
         return False
     rows = max(1, min(ctx.ny_local, chunk_nodes // max(problem.NX, 1)))

@@ -104,6 +104,26 @@ class OracleContext:
         self.f[:, y0:y0 + ny] = f
         self.fc = None
 
+    def init_analytic(self, fields, unit_density=False, unit_temperature=False, offeq=0, offeq_coef=0.0):
+        """what lbm_init_analytic evaluates, with the oracle's equilibrium: fields -> rho, u, T (+ off-equilibrium part)"""
+        e = []
+        for c0, terms in fields:
+            E = np.zeros((self.nx, self.ny)) + c0
+            for a, X, Y in terms:
+                E = E + a * np.outer(np.ones(self.nx) if X is None else X, np.ones(self.ny) if Y is None else Y)
+            e.append(np.ascontiguousarray(E.T))
+        rho = np.ones_like(e[0]) if unit_density else e[0]
+        T = np.ones_like(e[0]) if unit_temperature else e[3] / e[0]
+        f = np.stack(O.hermite_based_equilibrium(self.q, rho, e[1], e[2], T))
+        if offeq:
+            sxx, sxy, syy = e[4] + e[4], e[5] + e[6], e[7] + e[7]
+            kk = offeq_coef * rho if offeq == 2 else offeq_coef
+            for i in range(self.q.Q):
+                H = O.hermite(2, (int(self.q.cx[i]), int(self.q.cy[i])), self.q)
+                f[i] += self.q.w[i] * kk * (H[0][0] * sxx + H[0][1] * sxy + H[1][0] * sxy + H[1][1] * syy)
+        self.f[:] = f
+        self.fc = None
+
     # -- force --------------------------------------------------------------------------------
     def set_force_none(self):
         self.force = None

@@ -631,25 +631,67 @@ def test_row_chunked_upload_download(oracle):
                 b.download_f_rows(10, 8)
 
 
+INIT_STRATEGIES = ["ZeroVelocityInitialCondition", "AnalyticalEquilibrium", "ConstantDensity", "AnalyticalVelocityAndStress",
+                   "AnalyticalEquilibriumAndOffEquilibrium"]
+
+
+def _init_problems(q, qo, O):
+    sh = (1.0, 0.05, 1 / 6, 12, 10, (2 * np.pi, 2 * np.pi), False, 1.0, 1.0, 1.0, 1.0)
+    return [
+        (lbm.TGV(q, 0.8, 1, 12, 10), O.TGV(qo, 0.8, 1, 12, 10)),
+        (lbm.DecayingShearFlow.fields(*sh),
+         O.DecayingShearFlow(1 / 6, NX=12, NY=10, static=False, A=1.0, B=1.0, k_x=1.0, k_y=1.0, u_max=0.05, convenience=False)),
+        (lbm.TaylorGreenVortex(1 / 6, 1, 16, 16, static=False), O.TaylorGreenVortex(1 / 6, 1, 16, 16, static=False)),
+        (lbm.PoiseuilleFlow(1 / 6, 2), O.PoiseuilleFlow(1 / 6, 2)),
+        (lbm.CouetteFlow(1 / 6, 2), O.CouetteFlow(1 / 6, 2)),
+        (lbm.LinearizedTransverseShearWave(1 / 6, 1 / 6, 2), O.LinearizedTransverseShearWave(1 / 6, 1 / 6, 2)),
+    ]
+
+
 @pytest.mark.parametrize("name", LATTICES)
-def test_device_side_initialisation(name):
-    """lbm_init_equilibrium_rows == initialize(AnalyticalEquilibrium / ConstantDensity / ZeroVelocity)
-    evaluated on the host (hermite_based_equilibrium!, incl. T != 1 and the Val{4} quirk on D2Q37)."""
-    q = getattr(lbm.Quadratures, name)
-    problems = [lbm.TGV(q, 0.8, 1, 12, 10), lbm.DecayingShearFlow.fields(1.0, 0.05, 1 / 6, 12, 10, (2 * np.pi, 2 * np.pi), False, 1.0, 1.0, 1.0, 0.0)]
-    for pr in problems:
-        for strategy in (lbm.AnalyticalEquilibrium(), lbm.ConstantDensity(), lbm.ZeroVelocityInitialCondition()):
-            want = lbm.initialize(strategy, q, pr)
-            for dtype, tol in (("f64", 1e-14), ("f32", 1e-7)):
-                m = lbm.LatticeBoltzmannModel(pr, q, collision_model=lbm.SRT(0.8), initialization_strategy=strategy,
-                                              dtype=dtype, device_init=True)
-                got = m.f_stream
-                m.close()
-                dev = np.abs(want - q.weights).max() + 1e-30
-                if dtype == "f64":
-                    assert np.abs(got - want).max() <= tol * np.abs(want).max(), (name, type(strategy).__name__)
-                else:
-                    assert np.abs(got - want).max() <= 2e-7 * dev + 1e-12, (name, type(strategy).__name__)
+def test_device_side_initialisation(oracle, name):
+    """initialize(strategy, q, problem) evaluated on the device == the ORACLE's initialize (initial_conditions.jl:7-22,
+    analytical_offequilibrium.jl:10-87, analytical_velocity_stress.jl:5-31; hermite_based_equilibrium! incl. T != 1 and
+    the Val{4} quirk on D2Q37) for every closed-form strategy, through both device paths: lbm_init_analytic (separable
+    tables, the kernel evaluates rho, u, T and the off-equilibrium part) and lbm_init_equilibrium_rows (host rows)."""
+    O = oracle
+    q, qo = getattr(lbm.Quadratures, name), O.L.BY_NAME[name]()
+    from lbm.initial_conditions import initialize_on_device
+    for ph, po in _init_problems(q, qo, O):
+        for sname in INIT_STRATEGIES:
+            strategy = getattr(lbm, sname)()
+            want = np.asfortranarray(np.transpose(O.initialize(sname, qo, po), (2, 1, 0)))
+            dev = np.abs(want - q.weights).max() + 1e-30
+            for dtype in ("f64", "f32"):
+                for analytic in (True, False):
+                    if not analytic and sname.startswith("AnalyticalVelocityAndStress") or (not analytic and "OffEq" in sname):
+                        continue
+                    m = lbm.LatticeBoltzmannModel(ph, q, collision_model=lbm.SRT(0.8), initialization_strategy=lbm.ZeroVelocityInitialCondition(),
+                                                  dtype=dtype)
+                    launches = m.ctx.kernel_launches
+                    assert initialize_on_device(strategy, q, ph, m.ctx, analytic=analytic)
+                    assert m.ctx.kernel_launches > launches
+                    got = m.f_stream
+                    m.close()
+                    tag = (name, type(ph).__name__, sname, dtype, analytic)
+                    if dtype == "f64":
+                        assert np.abs(got - want).max() <= 1e-14 * np.abs(want).max(), tag
+                    else:
+                        assert np.abs(got - want).max() <= 2e-7 * dev + 1e-12, tag
+
+
+def test_device_side_initialisation_large_grid_and_model_flag(oracle):
+    """device_init=True on the model takes the analytic path (no host evaluation of the grid); 2048 x 1024 TGV with the
+    off-equilibrium part against the oracle."""
+    O = oracle
+    q, qo = lbm.D2Q9(), O.L.D2Q9()
+    ph, po = lbm.TGV(q, 0.8, 128, 2048, 1024), O.TGV(qo, 0.8, 128, 2048, 1024)
+    want = np.transpose(O.initialize("AnalyticalEquilibriumAndOffEquilibrium", qo, po), (2, 1, 0))
+    m = lbm.LatticeBoltzmannModel(ph, q, collision_model=lbm.TRT, initialization_strategy=lbm.AnalyticalEquilibriumAndOffEquilibrium(),
+                                  device_init=True)
+    got = m.f_stream
+    m.close()
+    assert np.abs(got - want).max() <= 1e-14 * np.abs(want).max()
 
 
 # ---------------------------------------------------------------------------------------------

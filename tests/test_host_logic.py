@@ -67,6 +67,48 @@ def test_initialize_matches_oracle(lattice, strategy):
         assert np.array_equal(part, fh[:, 3:7, :])
 
 
+@pytest.mark.parametrize("strategy", ["ZeroVelocityInitialCondition", "AnalyticalEquilibrium", "ConstantDensity",
+                                      "AnalyticalVelocityAndStress", "AnalyticalEquilibriumAndOffEquilibrium"])
+@pytest.mark.parametrize("lattice", ["D2Q9", "D2Q37"])
+def test_analytic_device_init_spec_matches_oracle(lattice, strategy):
+    """The separable tables + coefficients the host hands to lbm_init_analytic (O(NX + NY) evaluations of the problem's
+    pointwise functions) describe exactly initialize(strategy, q, problem): evaluated the way the kernel does (here by
+    the oracle-backed stand-in context) they reproduce the oracle's initialize for every problem and strategy."""
+    from _oracle_context import OracleContext
+    from lbm.initial_conditions import analytic_init_spec
+    q, qo = getattr(lbm.Quadratures, lattice), O.L.BY_NAME[lattice]()
+    for name, mk_h, mk_o in PAIRS:
+        ph, po = mk_h(q), mk_o(qo)
+        spec = analytic_init_spec(getattr(lbm, strategy)(), q, ph)
+        assert spec is not None, name
+        ctx = OracleContext(ph.NX, ph.NY, lattice, _abi.SRT, [1.0])
+        ctx.init_analytic(spec[0], **spec[1])
+        want = O.initialize(strategy, qo, po)
+        got = to_oracle_layout(ctx.download_f())
+        assert np.abs(got - want).max() <= 2e-15 * np.abs(want).max(), (name, np.abs(got - want).max())
+        # a slab of rows gets the same tables restricted to its rows
+        part = analytic_init_spec(getattr(lbm, strategy)(), q, ph, 2, 3)
+        c2 = OracleContext(ph.NX, 3, lattice, _abi.SRT, [1.0])
+        c2.init_analytic(part[0], **part[1])
+        assert np.abs(to_oracle_layout(c2.download_f()) - want[:, 2:5]).max() <= 2e-15 * np.abs(want).max(), name
+
+
+def test_decompose_function_refuses_rank_three_and_costs_lines_only():
+    from lbm.separable import decompose_function
+    xs, ys = np.linspace(0, 1, 300), np.linspace(0, 2, 200)
+    calls = []
+
+    def fn(X, Y):
+        calls.append(np.broadcast(X, Y).size)
+        return np.sin(3 * X) * np.cos(Y) + X * Y ** 2
+    c0, terms = decompose_function(fn, xs, ys)
+    R = sum(a * np.outer(X, Y) for a, X, Y in terms)
+    assert np.abs(R - fn(xs[:, None], ys[None, :])).max() < 1e-13
+    assert sum(calls[:-1]) < 48 * 48 + 6 * (300 + 200) + 4 * 512  # never the whole 300 x 200 grid
+    assert decompose_function(lambda X, Y: np.sin(X * Y) + np.exp(X + Y ** 2) + 1 / (1 + X + Y), xs, ys) is None
+    assert decompose_function(lambda X, Y: 0.0 * X, xs, ys) == (0.0, [])
+
+
 def test_forces_match_oracle():
     q, qo = lbm.D2Q9(), O.L.D2Q9()
     ph, po = lbm.PoiseuilleFlow(1 / 6, 2), O.PoiseuilleFlow(1 / 6, 2)
