@@ -203,6 +203,15 @@ typedef struct {
 } lbm_sep_field;
 int lbm_reduce_errors(lbm_ctx *ctx, double tau_visc, double u_max, const lbm_sep_field expected[8], double out[16]);
 
+/* The sums of process!(problem, q, f_in, time, stats) (src/processing_methods.jl:177-239, CompareWithAnalyticalSolution)
+ * for the local slab, on the device; expected[0..3] = density, velocity x / y, pressure of the problem at `time`
+ * (expected[4..7] are ignored).  out[0..11]:
+ *   0 sum rho   1 sum (ux+uy) rho   2 sum (kin + T)   3 sum kin, kin = (ux^2+uy^2) rho   4 sum T, T = p / rho
+ *   5 sum e_rho 6 sum e_rho (e_ux+e_uy) 7 sum (e_kin + e_T) 8 sum e_kin 9 sum e_T
+ *   10 sum |u - e_u|^2   11 sum (p - e_p)^2      with u = velocity / u_max, p = pressure(q, f, rho, u) (moments.jl:31-32);
+ * the caller multiplies 10, 11 by the cell area and takes the roots (processing_methods.jl:232-234, 254-255). */
+int lbm_reduce_process(lbm_ctx *ctx, double u_max, const lbm_sep_field expected[8], double out[16]);
+
 /* initialize(strategy, q, problem) (src/initial_conditions.jl:7-22) evaluated entirely on the device for the local slab:
  *   f_stream := hermite_based_equilibrium!(q, rho, u, T) [+ offeq_coef w_i [rho] dot(hermite(Val{2}, c_i, q), grad u + (grad u)')]
  * with the problem's analytic fields in the separable form of lbm_sep_field (x tables: nx entries, y tables: ny_local):

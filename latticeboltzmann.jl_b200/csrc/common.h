@@ -105,6 +105,7 @@ struct ErrorArgs {
     double *partials;    // [nblocks][16]
     double *out;         // [16] device
     int nblocks;
+    int mode;            // 0: TrackHydrodynamicErrors sums, 1: the sums of process! (CompareWithAnalyticalSolution)
 };
 
 // ----------------------------------------------------------------------------------------------

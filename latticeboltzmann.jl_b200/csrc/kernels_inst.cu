@@ -855,6 +855,25 @@ __device__ __forceinline__ void error_terms(double rho, double ux, double uy, do
     acc[13] += rho; acc[14] += rho * (vx + vy); acc[15] += rho * (vx * vx + vy * vy);
 }
 
+// One node's contribution to the sums of process! (processing_methods.jl:177-239, CompareWithAnalyticalSolution):
+//   0 rho  1 (ux+uy) rho  2 kin + T  3 kin = (ux^2+uy^2) rho  4 T = p / rho  (p = pressure(q, f, rho, u), moments.jl:31-32)
+//   5 e_rho  6 e_rho (e_ux+e_uy)  7 e_kin + e_T  8 e_kin = e_ux^2+e_uy^2  9 e_T = e_p / e_rho
+//   10 (ux-e_ux)^2 + (uy-e_uy)^2  11 (p-e_p)^2      (u dimensionless = u / u_max; the host applies the cell area)
+__device__ __forceinline__ void process_terms(double rho, double ux, double uy, double axx, double ayy, double u_max,
+                                              const double (&e)[8], double (&acc)[16]) {
+    double pr;
+    if constexpr (L::UNIT_PRESSURE) pr = 1.0;
+    else pr = ((axx + ayy) - rho * ((ux * ux + uy * uy) - 2)) / 2;
+    const double T = pr / rho;
+    const double vx = ux / u_max, vy = uy / u_max;
+    const double kin = (vx * vx + vy * vy) * rho;
+    acc[0] += rho; acc[1] += (vx + vy) * rho; acc[2] += kin + T; acc[3] += kin; acc[4] += T;
+    const double eT = e[3] / e[0], ekin = e[1] * e[1] + e[2] * e[2];
+    acc[5] += e[0]; acc[6] += e[0] * (e[1] + e[2]); acc[7] += ekin + eT; acc[8] += ekin; acc[9] += eT;
+    acc[10] += (vx - e[1]) * (vx - e[1]) + (vy - e[2]) * (vy - e[2]);
+    acc[11] += (pr - e[3]) * (pr - e[3]);
+}
+
 // TrackHydrodynamicErrors.next! (track_hydrodynamic_errors.jl:114-203) entirely on the device: per node
 // rho, u, p = tr(P)/D, sigma as in k_moments, scaled to dimensionless units, compared with the problem's
 // analytic fields given in separable form; 16 sums, deterministic two-stage reduction.
@@ -878,7 +897,8 @@ __global__ void __launch_bounds__(256) k_errors(const __grid_constant__ KParams<
                 const double *t0 = ea.tab + (size_t)(2 * f) * W, *t1 = t0 + W;
                 e[f] = ea.c0[f] + ea.a[f][0] * (__ldg(t0 + x) * __ldg(t0 + p.nx + y)) + ea.a[f][1] * (__ldg(t1 + x) * __ldg(t1 + p.nx + y));
             }
-            error_terms(rho, ux, uy, axx, axy, ayy, tau, ea.u_max, e, acc);
+            if (ea.mode == 0) error_terms(rho, ux, uy, axx, axy, ayy, tau, ea.u_max, e, acc);
+            else process_terms(rho, ux, uy, axx, ayy, ea.u_max, e, acc);
         }
     __shared__ double sm[16][8];
     const int lane = tid & 31, warp = tid >> 5;

@@ -1448,7 +1448,14 @@ int lbm_moments(lbm_ctx *c, double tau_visc, double *rho, double *ux, double *uy
     return p2p_check(c);
 }
 
+static int reduce_errors_mode(lbm_ctx *c, int mode, double tau_visc, double u_max, const lbm_sep_field *expected, double *out);
 int lbm_reduce_errors(lbm_ctx *c, double tau_visc, double u_max, const lbm_sep_field *expected, double *out) {
+    return reduce_errors_mode(c, 0, tau_visc, u_max, expected, out);
+}
+int lbm_reduce_process(lbm_ctx *c, double u_max, const lbm_sep_field *expected, double *out) {
+    return reduce_errors_mode(c, 1, 1.0, u_max, expected, out);
+}
+static int reduce_errors_mode(lbm_ctx *c, int mode, double tau_visc, double u_max, const lbm_sep_field *expected, double *out) {
     if (!c || !expected || !out) return fail(LBM_ERR_INVALID, "null argument");
     if (!(tau_visc > 0) || !(u_max > 0)) return fail(LBM_ERR_INVALID, "tau_visc %g, u_max %g", tau_visc, u_max);
     CU(cudaSetDevice(c->desc.device));
@@ -1482,6 +1489,7 @@ int lbm_reduce_errors(lbm_ctx *c, double tau_visc, double u_max, const lbm_sep_f
     ea.nblocks = nblocks;
     ea.tau_visc = tau_visc;
     ea.u_max = u_max;
+    ea.mode = mode;
     double h[16];
     if (e == cudaSuccess) {
         const bool pull = c->state == ST_COLLIDED;

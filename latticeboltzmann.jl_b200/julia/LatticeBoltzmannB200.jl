@@ -284,6 +284,59 @@ function next!(pm::TrackHydrodynamicErrors, m::B200Model, t::Int64)
     should_stop
 end
 
+# CompareWithAnalyticalSolution.next! / process! (processing_methods.jl:100-262): the 12 sums of process! come from one
+# device reduction (lbm_reduce_process); rho, u, p of the problem are passed in separable form like the error norms.
+host_visible(pm::CompareWithAnalyticalSolution, t) =
+    (mod(t, 100) == 0 && !(pm.stop_criteria isa NoStoppingCriteria)) || t == pm.n_steps || pm.should_process
+function sep_fields(fields::Vector{Matrix{Float64}})
+    decs = map(cross_decompose, fields)
+    any(isnothing, decs) && return nothing, nothing
+    keep = Vector{Float64}[]
+    sep = map(decs) do terms
+        a = [0.0, 0.0]; px = [Ptr{Float64}(C_NULL), Ptr{Float64}(C_NULL)]; py = copy(px)
+        for (k, (c, X, Y)) in enumerate(terms)
+            push!(keep, X, Y)
+            a[k] = c; px[k] = pointer(X); py[k] = pointer(Y)
+        end
+        LbmSepField(0.0, (a[1], a[2]), (px[1], px[2]), (py[1], py[2]))
+    end
+    sep, keep
+end
+function b200_process!(pm::CompareWithAnalyticalSolution, m::B200Model, time::Float64)
+    problem, q = pm.problem, m.quadrature
+    nx, ny = m.nx, m.ny
+    xr, yr = range(problem)
+    fields = Matrix{Float64}[zeros(nx, ny) for _ in 1:8]   # rho, ux, uy, p (the last four stay zero)
+    for xi in 1:nx, yi in 1:ny
+        x, y = xr[xi], yr[yi]
+        u = velocity(problem, x, y, time)
+        fields[1][xi, yi] = density(q, problem, x, y, time)
+        fields[2][xi, yi] = u[1]; fields[3][xi, yi] = u[2]
+        fields[4][xi, yi] = pressure(q, problem, x, y, time)
+    end
+    sep, keep = sep_fields(fields)
+    sep === nothing && return process!(problem, q, f_stream(m), time, pm.df)   # not separable: the reference's host path
+    s = zeros(16)
+    GC.@preserve keep check(ccall((:lbm_reduce_process, LIB), Cint, (Ptr{Cvoid}, Cdouble, Ptr{LbmSepField}, Ptr{Float64}),
+                                  m.ctx, problem.u_max, sep, s))
+    opp = Float64(yr.step) * Float64(xr.step)
+    push!(pm.df, (density = s[1], momentum = s[2], total_energy = s[3], kinetic_energy = s[4], internal_energy = s[5],
+                  density_a = s[6], momentum_a = s[7], total_energy_a = s[8], kinetic_energy_a = s[9], internal_energy_a = s[10],
+                  error_u = sqrt(opp * s[11]), error_p = sqrt(opp * s[12]),
+                  error_σ_xx = 0.0, error_σ_xy = 0.0, error_σ_yy = 0.0, error_σ_yx = 0.0))
+    false
+end
+function next!(pm::CompareWithAnalyticalSolution, m::B200Model, t::Int64)
+    time = t * delta_t(pm.problem)
+    if mod(t, 100) == 0 && should_stop!(pm.stop_criteria, m)
+        b200_process!(pm, m, time)
+        return true
+    end
+    (!pm.should_process && t != pm.n_steps) && return false
+    b200_process!(pm, m, time)
+    false
+end
+
 # simulate(model, time) (src/lattice_boltzmann_model.jl:60-77): the steps between two host-visible next! points are ONE
 # fused device batch (lbm_step); populations stay on the device throughout.
 function simulate(m::B200Model, time)

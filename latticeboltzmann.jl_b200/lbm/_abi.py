@@ -36,7 +36,7 @@ EXPORTS = [
     "lbm_set_force_none", "lbm_set_force_uniform", "lbm_set_force_field", "lbm_set_velocity_field",
     "lbm_set_force_separable",
     "lbm_collide", "lbm_stream", "lbm_apply_bcs", "lbm_step", "lbm_sync", "lbm_moments", "lbm_reduce",
-    "lbm_reduce_errors",
+    "lbm_reduce_errors", "lbm_reduce_process",
     "lbm_kernel_launches", "lbm_halo_path", "lbm_last_step_ms", "lbm_timer_start", "lbm_timer_stop", "lbm_set_option",
     "lbm_init_analytic",
     "lbm_batch_create", "lbm_batch_destroy", "lbm_batch_set_tau", "lbm_batch_set_force_uniform", "lbm_batch_upload_f",
@@ -126,6 +126,7 @@ def lib():
     l.lbm_moments.argtypes = [vp, C.c_double] + [vp] * 8
     l.lbm_reduce.argtypes = [vp, C.c_int32, dp, C.c_int32]
     l.lbm_reduce_errors.argtypes = [vp, C.c_double, C.c_double, C.POINTER(lbm_sep_field), dp]
+    l.lbm_reduce_process.argtypes = [vp, C.c_double, C.POINTER(lbm_sep_field), dp]
     l.lbm_kernel_launches.argtypes = [vp]
     l.lbm_kernel_launches.restype = C.c_int64
     l.lbm_halo_path.argtypes = [vp]
@@ -370,24 +371,21 @@ class Context:
     def reduce_errors(self, tau_visc, u_max, expected):
         """expected: 8 tuples (c0, [(a, X or None, Y or None), ...up to 2 terms]) for
         rho, ux, uy, p, sxx, sxy, syx, syy; X has NX entries, Y has NY_local.  Returns the 16 local sums."""
-        arr = (lbm_sep_field * 8)()
-        keep = []
-        for f, (c0, terms) in enumerate(expected):
-            arr[f].c0 = float(c0)
-            if len(terms) > 2:
-                raise ValueError("at most two separable terms per field")
-            for k, (a, X, Y) in enumerate(terms):
-                arr[f].a[k] = float(a)
-                for name, tab, n in (("x", X, self.nx), ("y", Y, self.ny_local)):
-                    if tab is not None:
-                        t = np.ascontiguousarray(tab, dtype=np.float64)
-                        if t.shape != (n,):
-                            raise ValueError(f"separable table '{name}' must have {n} entries")
-                        keep.append(t)
-                        getattr(arr[f], name)[k] = t.ctypes.data
+        arr, keep = _sep_fields(expected, self.nx, self.ny_local)
         out = (C.c_double * 16)()
         check(lib().lbm_reduce_errors(self._h, float(tau_visc), float(u_max), arr, out))
+        del keep
         return np.array(out[:])
+
+    def reduce_process(self, u_max, expected):
+        """The 12 local sums of process! (CompareWithAnalyticalSolution; see lbm_reduce_process).  expected: the first
+        four separable fields of reduce_errors (rho, ux, uy, p); further entries are ignored."""
+        expected = list(expected[:4]) + [(0.0, [])] * 4
+        arr, keep = _sep_fields(expected, self.nx, self.ny_local)
+        out = (C.c_double * 16)()
+        check(lib().lbm_reduce_process(self._h, float(u_max), arr, out))
+        del keep
+        return np.array(out[:12])
 
     # ---- introspection -------------------------------------------------------------------
     @property

@@ -11,7 +11,7 @@ import warnings
 import numpy as np
 
 from . import _abi
-from .separable import separable_from_fields
+from .separable import decompose_function, separable_from_fields
 from .problems import (CouetteFlow, DecayingShearFlow, LidDrivenCavityFlow, PoiseuilleFlow, TGV,
                        TaylorGreenVortex)
 
@@ -168,12 +168,20 @@ class TrackHydrodynamicErrors(ProcessingMethodBase):
         tau = q.speed_of_sound_squared * pr.lattice_viscosity()
         sep = pr.expected_separable(q, time, state.y0, state.ny_local) if self.device_norms else None
         if sep is None and self.device_norms:
-            # no analytic separable form: recover one from the fields sampled on the grid (exact for rank <= 2)
-            X, Y = pr.grid(state.y0, state.ny_local)
-            e_ux, e_uy = pr.velocity(X, Y, time)
-            (e_sxx, e_sxy), (e_syx, e_syy) = pr.deviatoric_tensor(q, X, Y, time)
-            sep = separable_from_fields([np.asarray(a, dtype=np.float64) * np.ones_like(X) for a in (
-                pr.density(q, X, Y, time), e_ux, e_uy, pr.pressure(q, X, Y, time), e_sxx, e_sxy, e_syx, e_syy)])
+            # no analytic separable form: recover one from O(NX + NY) evaluations of the pointwise fields (exact for
+            # rank <= 2), falling back to the fields sampled on the whole grid
+            xs, ys = pr._xy(state.y0, state.ny_local)
+            dev = lambda a, b: (lambda X, Y: pr.deviatoric_tensor(q, X, Y, time)[a][b])  # noqa: E731
+            sep = [decompose_function(fn, xs, ys) for fn in (
+                lambda X, Y: pr.density(q, X, Y, time), lambda X, Y: pr.velocity(X, Y, time)[0],
+                lambda X, Y: pr.velocity(X, Y, time)[1], lambda X, Y: pr.pressure(q, X, Y, time),
+                dev(0, 0), dev(0, 1), dev(1, 0), dev(1, 1))]
+            if any(d is None for d in sep):
+                X, Y = pr.grid(state.y0, state.ny_local)
+                e_ux, e_uy = pr.velocity(X, Y, time)
+                (e_sxx, e_sxy), (e_syx, e_syy) = pr.deviatoric_tensor(q, X, Y, time)
+                sep = separable_from_fields([np.asarray(a, dtype=np.float64) * np.ones_like(X) for a in (
+                    pr.density(q, X, Y, time), e_ux, e_uy, pr.pressure(q, X, Y, time), e_sxx, e_sxy, e_syx, e_syy)])
         if sep is not None:
             # all 16 sums on the device (lbm_reduce_errors); nothing but scalars crosses PCIe
             s = state.allreduce(state.ctx.reduce_errors(tau, pr.u_max, sep))
@@ -237,10 +245,19 @@ class CompareWithAnalyticalSolution(ProcessingMethodBase):
         return False
 
 
-def process_(problem, q, state, time, stats, should_visualize=False):
+def process_(problem, q, state, time, stats, should_visualize=False, device_sums=True):
     """process!(problem, q, f_in, time, stats) (processing_methods.jl:142-269)."""
     pr = problem
     xstep, ystep = pr.range_steps()
+    opp = ystep * xstep
+    sep = _process_separable(pr, q, time, state) if device_sums else None
+    if sep is not None:
+        # all 12 sums on the device (lbm_reduce_process): only scalars cross PCIe
+        s = state.allreduce(state.ctx.reduce_process(pr.u_max, sep))
+        s[10] *= opp
+        s[11] *= opp
+        stats.append(_process_row(s))
+        return False
     h = state.moments(1.0, ("rho", "ux", "uy", "p"))
     rho, p = h["rho"], h["p"]
     T = p / rho
@@ -252,17 +269,39 @@ def process_(problem, q, state, time, stats, should_visualize=False):
     e_ux, e_uy = pr.velocity(X, Y, time)
     e_T = e_p / e_rho
     e_kin = e_ux ** 2 + e_uy ** 2
-    opp = ystep * xstep
     s = state.allreduce(np.array([
         np.sum(rho), np.sum((ux + uy) * rho), np.sum(kin + T), np.sum(kin), np.sum(T),
         np.sum(e_rho), np.sum(e_rho * (e_ux + e_uy)), np.sum(e_kin + e_T), np.sum(e_kin), np.sum(e_T),
         np.sum(opp * ((ux - e_ux) ** 2 + (uy - e_uy) ** 2)), np.sum(opp * (p - e_p) ** 2)]))
-    stats.append(dict(
+    stats.append(_process_row(s))
+    return False
+
+
+def _process_row(s):
+    return dict(
         density=s[0], momentum=s[1], total_energy=s[2], kinetic_energy=s[3], internal_energy=s[4],
         density_a=s[5], momentum_a=s[6], total_energy_a=s[7], kinetic_energy_a=s[8], internal_energy_a=s[9],
         error_u=float(np.sqrt(s[10])), error_p=float(np.sqrt(s[11])),
-        error_sxx=0.0, error_sxy=0.0, error_syy=0.0, error_syx=0.0))
-    return False
+        error_sxx=0.0, error_sxy=0.0, error_syy=0.0, error_syx=0.0)
+
+
+def _process_separable(pr, q, time, state):
+    """rho, ux, uy, p of the problem at `time` in separable form for the local slab: the problem's own closed form when it
+    has one, else a cross approximation from O(NX + NY) evaluations of its pointwise functions; None if not of rank <= 2."""
+    if not hasattr(state.ctx, "reduce_process"):
+        return None
+    sep = pr.expected_separable(q, time, state.y0, state.ny_local)
+    if sep is not None:
+        return sep[:4]
+    xs, ys = pr._xy(state.y0, state.ny_local)
+    out = []
+    for fn in (lambda X, Y: pr.density(q, X, Y, time), lambda X, Y: pr.velocity(X, Y, time)[0],
+               lambda X, Y: pr.velocity(X, Y, time)[1], lambda X, Y: pr.pressure(q, X, Y, time)):
+        d = decompose_function(fn, xs, ys)
+        if d is None:
+            return None
+        out.append(d)
+    return out
 
 
 class TakeSnapshots(ProcessingMethodBase):

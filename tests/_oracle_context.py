@@ -236,6 +236,24 @@ class OracleContext:
         return np.array([np.sum(x) for x in s])
 
 
+    def reduce_process(self, u_max, expected):
+        """the 12 sums of process! (processing_methods.jl:177-239) from the oracle's moments"""
+        h = self._fields(1.0)
+        e = []
+        for c0, terms in expected[:4]:
+            v = c0 + np.zeros((self.ny, self.nx))
+            for a, X, Y in terms:
+                xs = np.ones(self.nx) if X is None else np.asarray(X, dtype=np.float64)
+                ys = np.ones(self.ny) if Y is None else np.asarray(Y, dtype=np.float64)
+                v = v + a * (ys[:, None] * xs[None, :])
+            e.append(v)
+        rho, vx, vy, pr = h["rho"], h["ux"] / u_max, h["uy"] / u_max, h["p"]
+        T, kin = pr / rho, (vx ** 2 + vy ** 2) * rho
+        eT, ekin = e[3] / e[0], e[1] ** 2 + e[2] ** 2
+        s = [rho, (vx + vy) * rho, kin + T, kin, T, e[0], e[0] * (e[1] + e[2]), ekin + eT, ekin, eT,
+             (vx - e[1]) ** 2 + (vy - e[2]) ** 2, (pr - e[3]) ** 2]
+        return np.array([np.sum(x) for x in s])
+
 @contextlib.contextmanager
 def emulated_backend(monkeypatch):
     """Route lbm.model.make_context to the oracle-backed context for the duration of a test."""

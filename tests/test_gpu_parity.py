@@ -767,10 +767,77 @@ def test_couette_moving_wall_steady_state(oracle, name):
     O.simulate_model(mo, range(0, n_steps + 1))
     got, want = pm.df[-1], mo.pm.df[-1]
     assert len(pm.df) == len(mo.pm.df)
-    for k in ("error_u", "error_p", "density", "momentum", "kinetic_energy"):
+    for k in want:  # all 16 columns of process! (processing_methods.jl:241-262); the 12 sums come from lbm_reduce_process
         assert abs(got[k] - want[k]) <= 1e-9 * abs(want[k]) + 1e-14, (name, k, got[k], want[k])
     assert rel_max(to_oracle_layout(model.f_stream), mo.f_stream) < 1e-12
     model.close()
+
+
+@pytest.mark.parametrize("kind", ["LinearizedThermalDiffusion", "LinearizedTransverseShearWave"])
+@pytest.mark.parametrize("name,model", [("D2Q9", "SRT"), ("D2Q9", "MRT"), ("D2Q17", "TRT"), ("D2Q37", "MRT")])
+def test_linearized_hydrodynamic_modes(oracle, kind, name, model):
+    """The Linearized* problems (src/problems/linear_hydrodynamics_modes.jl; Shan & Chen's linear modes: a density /
+    temperature wave with T = rho_0 theta_0 / rho != 1, and a transverse shear wave) through simulate(problem, q) on the
+    device against the oracle: populations after every batch boundary and every row of the statistics."""
+    O = oracle
+    q, qo = getattr(lbm.Quadratures, name), O.L.BY_NAME[name]()
+    cm = {"SRT": lbm.SRT, "TRT": lbm.TRT, "MRT": lbm.MRT}[model]
+    nu = 0.4 / q.speed_of_sound_squared
+    ph, po = getattr(lbm, kind)(nu, nu, 2), getattr(O, kind)(nu, nu, 2)
+    n_steps = 120
+    pm = lbm.ProcessingMethod(ph, True, n_steps)
+    assert isinstance(pm, lbm.CompareWithAnalyticalSolution)
+    m = lbm.LatticeBoltzmannModel(ph, q, collision_model=cm, process_method=pm)
+    lbm.simulate(m, range(0, n_steps + 1))
+    mo = O.make_model(po, qo, model, pm=O.processing_method(po, True, n_steps))
+    O.simulate_model(mo, range(0, n_steps + 1))
+    assert rel_max(to_oracle_layout(m.f_stream), mo.f_stream) < 1e-12
+    assert len(pm.df) == len(mo.pm.df)
+    for got, want in zip(pm.df, mo.pm.df):
+        for k in want:
+            assert abs(got[k] - want[k]) <= 1e-10 * abs(want[k]) + 1e-15, (kind, name, model, k, got[k], want[k])
+    m.close()
+    # Float32 storage: populations within 1e-5 of the oracle
+    m = lbm.LatticeBoltzmannModel(ph, q, collision_model=cm, process_method=lbm.ProcessingMethod(ph, False, n_steps), dtype="f32")
+    lbm.simulate(m, range(0, n_steps + 1))
+    assert rel_max(to_oracle_layout(m.f_stream), mo.f_stream) < 1e-5
+    m.close()
+
+
+@pytest.mark.parametrize("name", ["D2Q4", "D2Q9", "D2Q21", "D2Q37"])
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_process_sums_on_device_match_oracle(oracle, name, dtype):
+    """process! with should_process = true (CompareWithAnalyticalSolution, processing_methods.jl:177-262): every row of
+    the statistics comes from ONE device reduction (lbm_reduce_process) and equals the oracle's row; the launch count
+    shows no field download (k_moments) happened."""
+    O = oracle
+    q, qo = getattr(lbm.Quadratures, name), O.L.BY_NAME[name]()
+    nu = 0.3 / q.speed_of_sound_squared
+    for mk_h, mk_o in ((lambda: lbm.PoiseuilleFlow(nu, 2), lambda: O.PoiseuilleFlow(nu, 2)),
+                       (lambda: lbm.CouetteFlow(nu, 2), lambda: O.CouetteFlow(nu, 2))):
+        problem, po = mk_h(), mk_o()
+        n_steps = 40
+        pm = lbm.CompareWithAnalyticalSolution(problem, True, n_steps, lbm.NoStoppingCriteria())
+        model = lbm.LatticeBoltzmannModel(problem, q, collision_model=lbm.TRT, process_method=pm, dtype=dtype,
+                                          initialization_strategy=lbm.ZeroVelocityInitialCondition())
+        lbm.simulate(model, range(0, n_steps + 1))
+        mo = O.make_model(po, qo, "TRT", strategy="ZeroVelocityInitialCondition",
+                          pm=O.CompareWithAnalyticalSolution(po, True, n_steps, O.NoStoppingCriteria()))
+        O.simulate_model(mo, range(0, n_steps + 1))
+        assert len(pm.df) == len(mo.pm.df) == n_steps + 1
+        tol = 1e-10 if dtype == "f64" else 2e-5
+        for got, want in zip(pm.df, mo.pm.df):
+            for k in want:
+                assert abs(got[k] - want[k]) <= tol * abs(want[k]) + (1e-14 if dtype == "f64" else 1e-9), (name, k, got[k], want[k])
+        # host-path rows (fields downloaded, numpy sums) agree as well
+        pm2 = lbm.CompareWithAnalyticalSolution(problem, True, 3, lbm.NoStoppingCriteria())
+        from lbm.processing_methods import process_
+        rows = []
+        process_(problem, q, model.state, 0.0, rows, device_sums=True)
+        process_(problem, q, model.state, 0.0, rows, device_sums=False)
+        for k in rows[0]:
+            assert abs(rows[0][k] - rows[1][k]) <= 1e-11 * abs(rows[1][k]) + 1e-14, (k, rows[0][k], rows[1][k])
+        model.close()
 
 
 @pytest.mark.parametrize("name", ["D2Q9", "D2Q17", "D2Q37"])
