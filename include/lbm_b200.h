@@ -230,6 +230,22 @@ typedef struct {
 } lbm_init_spec;
 int lbm_init_analytic(lbm_ctx *ctx, const lbm_init_spec *spec);
 
+/* Page-locked host memory for population arrays that cross the boundary often (snapshots, array-level operators): copies
+ * from / to such arrays run at the full PCIe rate and asynchronously.  Plain malloc'ed arrays are accepted everywhere. */
+int lbm_host_alloc(void **ptr, size_t bytes);
+int lbm_host_free(void *ptr);
+
+/* TakeSnapshots.next! (src/processing_methods/take_snapshots.jl:12-29: push!(snapshots, copy(f_in))) without stalling the
+ * step loop.  lbm_snapshot_begin enqueues one kernel that writes f_stream of the current state into a compact device
+ * buffer (the ping-pong buffers and the fused state machine are not disturbed: no materialisation, no extra collide-only
+ * launch afterwards) and a device-to-host copy on a separate copy stream, then returns; lbm_step calls that follow run
+ * concurrently with the copy.  lbm_snapshot_end waits for the copy; `f` ([Q][NY_local][NX] doubles, the layout of
+ * lbm_download_f) must stay valid until then.  Page-locked `f` (lbm_host_alloc) receives the copy directly; otherwise the
+ * library stages through its own page-locked buffer and lbm_snapshot_end does the final host copy.  At most one snapshot
+ * is in flight per context: a second lbm_snapshot_begin first completes the previous one. */
+int lbm_snapshot_begin(lbm_ctx *ctx, double *f);
+int lbm_snapshot_end(lbm_ctx *ctx);
+
 /* Introspection used by bench.py / tests. */
 int64_t lbm_kernel_launches(const lbm_ctx *ctx); /* kernels launched by this context so far */
 /* How halos travel between y-slabs: 0 = single GPU (ghost cells written by the kernels themselves), 1 = NCCL

@@ -90,7 +90,9 @@ struct ReduceArgs {
     double *partials;  // [nblocks][4]
     double *u_old;     // [2][nyl][nx] for LBM_REDUCE_VELOCITY_CHANGE
     double *out;       // [4] device
-    int nblocks;
+    int nblocks;       // capacity of `partials` (the launcher replaces it by the grid size)
+    int rows_per_cta;  // set by the launcher
+    long long zero;    // 0 (run-time constant for after_load)
 };
 
 // Expected (analytic) fields for the on-device error norms, in separable form
@@ -104,7 +106,8 @@ struct ErrorArgs {
     double u_max;        // dimensionless_velocity / dimensionless_stress scaling
     double *partials;    // [nblocks][16]
     double *out;         // [16] device
-    int nblocks;
+    int nblocks;         // capacity of `partials` (the launcher replaces it by the grid size)
+    int rows_per_cta;    // set by the launcher
     int mode;            // 0: TrackHydrodynamicErrors sums, 1: the sums of process! (CompareWithAnalyticalSolution)
 };
 
@@ -214,6 +217,9 @@ struct Ops {
     void (*init_eq32)(const KParams<float> &p, const double *rho, const double *ux, const double *uy, const double *T, cudaStream_t s);
     void (*init_analytic64)(const KParams<double> &p, const InitArgs &ia, cudaStream_t s);
     void (*init_analytic32)(const KParams<float> &p, const InitArgs &ia, cudaStream_t s);
+    // f_stream of the current state as compact Float64 [Q][nyl][nx] (pull: the state holds post-collision populations)
+    void (*snapshot64)(bool pull, const KParams<double> &p, double *out, cudaStream_t s);
+    void (*snapshot32)(bool pull, const KParams<float> &p, double *out, cudaStream_t s);
     // persistent multi-step kernel: co-resident grid (CTAs, threads) for this <collision model, dtype>, 0 CTAs if the
     // device cannot launch cooperatively; pa: src = current state, pb: the two buffers swapped
     void (*persist_grid64)(int cm, bool p2p, int *ctas, int *threads);

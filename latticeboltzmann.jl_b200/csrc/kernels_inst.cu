@@ -785,64 +785,123 @@ __global__ void __launch_bounds__(256) k_moments(const __grid_constant__ KParams
     }
 }
 
-// deterministic two-stage reduction of up to 4 per-node quantities
+// TakeSnapshots (take_snapshots.jl:12-29): f_stream of the current state as compact Float64 [Q][nyl][nx] (the host array's
+// memory order) WITHOUT touching the ping-pong buffers: from post-collision populations the stream + BC step happens in
+// the load, exactly as for the diagnostics.  The D2H copy of `out` then runs on a copy stream under the next steps.
 template <typename T, bool PULL>
-__global__ void __launch_bounds__(256) k_reduce(const __grid_constant__ KParams<T> p, const ReduceArgs ra) {
-    double acc[4] = {0, 0, 0, 0};
+__global__ void __launch_bounds__(256) k_snapshot(const __grid_constant__ KParams<T> p, double *__restrict__ out) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= p.nx) return;
+    const long long N = (long long)p.nyl * p.nx;
+    for (int y = blockIdx.y * blockDim.y + threadIdx.y; y < p.nyl; y += gridDim.y * blockDim.y) {
+        T f[Q];
+        load_node<T, PULL>(p, x, y, f);
+        const long long n = (long long)y * p.nx + x;
+        static_for<0, Q>([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            if constexpr (Shifted<T>::value) out[i * N + n] = (double)f[i] + c_lat64.w[i];
+            else out[i * N + n] = (double)f[i];
+        });
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Reducing diagnostics.  Geometry (launch_reduce / launch_errors): the CTA covers blockDim.x columns and `rows_per_cta`
+// consecutive rows; a thread keeps its column and walks the CTA's rows (stride blockDim.y) accumulating in registers,
+// then warp shuffles -> shared memory -> one partial per CTA and sum, folded by k_final_sum in a fixed order
+// (deterministic: no atomics, the result depends only on the grid size).  rows_per_cta is a handful of rows, so a 4096^2
+// grid runs thousands of CTAs and the loads of successive rows overlap (the loop has no aliasing stores).
+// ------------------------------------------------------------------------------------------
+template <int NS>
+__device__ __forceinline__ void cta_partials(const double (&acc)[NS], double *__restrict__ partials) {
+    __shared__ double sm[NS][8];
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-    for (int y = blockIdx.y * blockDim.y + threadIdx.y; y < p.nyl; y += gridDim.y * blockDim.y)
-        for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < p.nx; x += gridDim.x * blockDim.x) {
-            double rho, ux, uy, axx, axy, ayy;
-            node_fields<T, PULL>(p, x, y, rho, ux, uy, axx, axy, ayy);
-            const long long n = (long long)y * p.nx + x;
-            if (ra.kind == LBM_REDUCE_MEAN_UX) {
-                acc[0] += ux; acc[1] += 1.0; acc[2] += (ux != ux) ? 1.0 : 0.0;
-            } else if (ra.kind == LBM_REDUCE_VELOCITY_CHANGE) {
-                const long long N = (long long)p.nyl * p.nx;
-                const double ox = ra.u_old[n], oy = ra.u_old[N + n];
-                acc[0] += ((ux - ox) * (ux - ox) + (uy - oy) * (uy - oy));
-                acc[1] += ox * ox + oy * oy;
-                ra.u_old[n] = ux; ra.u_old[N + n] = uy;
-            } else if (ra.kind == LBM_REDUCE_DENSITY_CHANGE) {
-                const double o = ra.u_old[n];
-                acc[0] += (rho - o) * (rho - o);
-                if (x == p.nx - 1 && p.y0g + y == p.nyg - 1) acc[1] += rho;
-                ra.u_old[n] = rho;
-            } else {
-                acc[0] += rho; acc[1] += rho * (ux + uy); acc[2] += rho * (ux * ux + uy * uy);
-            }
-        }
-    __shared__ double sm[4][8];
     const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < NS; ++k) {
         double v = acc[k];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
         if (lane == 0) sm[k][warp] = v;
     }
     __syncthreads();
-    if (tid < 4) {
+    if (tid < NS) {
         const int nw = (blockDim.x * blockDim.y + 31) >> 5;
         double v = 0;
         for (int w = 0; w < nw; ++w) v += sm[tid][w];
-        ra.partials[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 4 + tid] = v;
+        partials[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * NS + tid] = v;
     }
 }
+
+// `v` with a numerically void data dependence on `loaded` (zero == 0 at run time, opaque to the compiler).  Used where a
+// value is stored to the address another value was just loaded from: without the dependence the store is issued while the
+// load of the same sector is still in flight, and B200 serialises that -- the velocity-change reduction ran at 1.4-1.9 ms
+// per 4096^2 instead of 0.28 ms (tools/microbench/rmw_reduce.cu, profiles/r02/microbench_rmw_reduce.jsonl).
+__device__ __forceinline__ double after_load(double v, double loaded, long long zero) {
+    return __longlong_as_double(__double_as_longlong(v) | (__double_as_longlong(loaded) & zero));
+}
+
+// up to 4 per-node quantities (stop criteria, conserved sums); KIND is a compile-time lbm_reduce_kind
+template <typename T, bool PULL, int KIND>
+__global__ void __launch_bounds__(256, 3) k_reduce(const __grid_constant__ KParams<T> p, const ReduceArgs ra) {
+    double acc[4] = {0, 0, 0, 0};
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y0 = blockIdx.y * ra.rows_per_cta, y1 = min(p.nyl, y0 + ra.rows_per_cta);
+    double *__restrict__ old = ra.u_old;
+    const long long N = (long long)p.nyl * p.nx;
+    if (x < p.nx) {
+#pragma unroll 2
+        for (int y = y0 + threadIdx.y; y < y1; y += blockDim.y) {
+            double rho, ux, uy, axx, axy, ayy;
+            node_fields<T, PULL>(p, x, y, rho, ux, uy, axx, axy, ayy);
+            const long long n = (long long)y * p.nx + x;
+            if constexpr (KIND == LBM_REDUCE_MEAN_UX) {
+                acc[0] += ux; acc[1] += 1.0; acc[2] += (ux != ux) ? 1.0 : 0.0;
+            } else if constexpr (KIND == LBM_REDUCE_VELOCITY_CHANGE) {
+                const double ox = old[n], oy = old[N + n];
+                acc[0] += ((ux - ox) * (ux - ox) + (uy - oy) * (uy - oy));
+                acc[1] += ox * ox + oy * oy;
+                old[n] = after_load(ux, ox, ra.zero); old[N + n] = after_load(uy, oy, ra.zero);
+            } else if constexpr (KIND == LBM_REDUCE_DENSITY_CHANGE) {
+                const double o = old[n];
+                acc[0] += (rho - o) * (rho - o);
+                if (x == p.nx - 1 && p.y0g + y == p.nyg - 1) acc[1] += rho;
+                old[n] = after_load(rho, o, ra.zero);
+            } else {
+                acc[0] += rho; acc[1] += rho * (ux + uy); acc[2] += rho * (ux * ux + uy * uy);
+            }
+        }
+    }
+    cta_partials<4>(acc, ra.partials);
+}
+
+// Division by a launch-wide constant.  exact mode divides like the reference; fast mode multiplies by the reciprocal
+// computed once per thread (<= 1 ulp per operation, a Float64 division is ~10 FP64-pipe instructions).
+struct InvConst {
+    double d, inv;
+    __device__ __forceinline__ explicit InvConst(double d_) : d(d_), inv(1.0 / d_) {}
+    __device__ __forceinline__ double div(double x) const {
+#if LBM_FAST
+        return x * inv;
+#else
+        return x / d;
+#endif
+    }
+};
 
 // One node's contribution to the 16 sums of TrackHydrodynamicErrors.next! (track_hydrodynamic_errors.jl:134-203):
 // rho, u, p = tr(P)/D, sigma as in k_moments, scaled to dimensionless units, against the expected fields e[8] =
 // rho, ux, uy, p, sxx, sxy, syx, syy.
-__device__ __forceinline__ void error_terms(double rho, double ux, double uy, double axx, double axy, double ayy, double tau,
-                                            double u_max, const double (&e)[8], double (&acc)[16]) {
-    const double den = 1 + 1 / (2 * tau), fac = 1 / (u_max * u_max);
+__device__ __forceinline__ void error_terms(double rho, double ux, double uy, double axx, double axy, double ayy, double half_inv_tau,
+                                            const InvConst &den, const InvConst &u_max, double fac, const double (&e)[8],
+                                            double (&acc)[16]) {
     const double exx = rho * (ux * ux), exy = rho * (ux * uy), eyy = rho * (uy * uy);
-    const double bxx = (axx + (1 / (2 * tau)) * exx) / den, byy = (ayy + (1 / (2 * tau)) * eyy) / den;
+    const double bxx = den.div(axx + half_inv_tau * exx), byy = den.div(ayy + half_inv_tau * eyy);
     const double pr = ((bxx - rho * (ux * ux - 1)) + (byy - rho * (uy * uy - 1))) / 2;
-    double sxx = (axx - exx) / den, sxy = (axy - exy) / den, syy = (ayy - eyy) / den;
+    double sxx = den.div(axx - exx), sxy = den.div(axy - exy), syy = den.div(ayy - eyy);
     const double tr = (sxx + syy) / 2;
     sxx = (sxx - tr) * fac; syy = (syy - tr) * fac; sxy = sxy * fac;
-    const double vx = ux / u_max, vy = uy / u_max;
+    const double vx = u_max.div(ux), vy = u_max.div(uy);
     acc[0] += (rho - e[0]) * (rho - e[0]);
     acc[1] += (vx - e[1]) * (vx - e[1]) + (vy - e[2]) * (vy - e[2]);
     acc[2] += e[1] * e[1] + e[2] * e[2];
@@ -859,13 +918,13 @@ __device__ __forceinline__ void error_terms(double rho, double ux, double uy, do
 //   0 rho  1 (ux+uy) rho  2 kin + T  3 kin = (ux^2+uy^2) rho  4 T = p / rho  (p = pressure(q, f, rho, u), moments.jl:31-32)
 //   5 e_rho  6 e_rho (e_ux+e_uy)  7 e_kin + e_T  8 e_kin = e_ux^2+e_uy^2  9 e_T = e_p / e_rho
 //   10 (ux-e_ux)^2 + (uy-e_uy)^2  11 (p-e_p)^2      (u dimensionless = u / u_max; the host applies the cell area)
-__device__ __forceinline__ void process_terms(double rho, double ux, double uy, double axx, double ayy, double u_max,
+__device__ __forceinline__ void process_terms(double rho, double ux, double uy, double axx, double ayy, const InvConst &u_max,
                                               const double (&e)[8], double (&acc)[16]) {
     double pr;
     if constexpr (L::UNIT_PRESSURE) pr = 1.0;
     else pr = ((axx + ayy) - rho * ((ux * ux + uy * uy) - 2)) / 2;
     const double T = pr / rho;
-    const double vx = ux / u_max, vy = uy / u_max;
+    const double vx = u_max.div(ux), vy = u_max.div(uy);
     const double kin = (vx * vx + vy * vy) * rho;
     acc[0] += rho; acc[1] += (vx + vy) * rho; acc[2] += kin + T; acc[3] += kin; acc[4] += T;
     const double eT = e[3] / e[0], ekin = e[1] * e[1] + e[2] * e[2];
@@ -874,65 +933,64 @@ __device__ __forceinline__ void process_terms(double rho, double ux, double uy, 
     acc[11] += (pr - e[3]) * (pr - e[3]);
 }
 
-// TrackHydrodynamicErrors.next! (track_hydrodynamic_errors.jl:114-203) entirely on the device: per node
+// TrackHydrodynamicErrors.next! (track_hydrodynamic_errors.jl:114-203) / process! entirely on the device: per node
 // rho, u, p = tr(P)/D, sigma as in k_moments, scaled to dimensionless units, compared with the problem's
-// analytic fields given in separable form; 16 sums, deterministic two-stage reduction.
+// analytic fields given in separable form; 16 sums, deterministic two-stage reduction (geometry: see k_reduce).
 //   0 (rho-e)^2  1 |u-e|^2  2 |e_u|^2  3 (p-e)^2  4 e_p^2  5 (e_sxx-sxx)^2  6 e_sxx^2  7 (e_sxy-sxy)^2  8 e_sxy^2
 //   9 (e_syy-syy)^2  10 e_syy^2  11 (e_syx-syx)^2  12 e_syx^2  13 rho  14 rho (ux+uy)  15 rho (ux^2+uy^2)
-template <typename T, bool PULL>
-__global__ void __launch_bounds__(256) k_errors(const __grid_constant__ KParams<T> p, const __grid_constant__ ErrorArgs ea) {
+// MODE 0: those sums, MODE 1: the sums of process!.  Terms whose coefficient is zero (most fields of most problems have
+// one term or none) are skipped by a launch-uniform branch, so their tables are never read.
+template <typename T, bool PULL, int MODE>
+__global__ void __launch_bounds__(256, 2) k_errors(const __grid_constant__ KParams<T> p, const __grid_constant__ ErrorArgs ea) {
     double acc[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) acc[k] = 0;
-    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
     const int W = p.nx + p.nyl;
-    const double tau = ea.tau_visc;
-    for (int y = blockIdx.y * blockDim.y + threadIdx.y; y < p.nyl; y += gridDim.y * blockDim.y)
-        for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < p.nx; x += gridDim.x * blockDim.x) {
+    const double half_inv_tau = 1 / (2 * ea.tau_visc);
+    const InvConst den(1 + 1 / (2 * ea.tau_visc)), u_max(ea.u_max);
+    const double fac = 1 / (ea.u_max * ea.u_max);
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y0 = blockIdx.y * ea.rows_per_cta, y1 = min(p.nyl, y0 + ea.rows_per_cta);
+    if (x < p.nx) {
+        const double *__restrict__ tab = ea.tab;
+#pragma unroll 2
+        for (int y = y0 + threadIdx.y; y < y1; y += blockDim.y) {
             double rho, ux, uy, axx, axy, ayy;
             node_fields<T, PULL>(p, x, y, rho, ux, uy, axx, axy, ayy);
             double e[8];
 #pragma unroll
             for (int f = 0; f < 8; ++f) {
-                const double *t0 = ea.tab + (size_t)(2 * f) * W, *t1 = t0 + W;
-                e[f] = ea.c0[f] + ea.a[f][0] * (__ldg(t0 + x) * __ldg(t0 + p.nx + y)) + ea.a[f][1] * (__ldg(t1 + x) * __ldg(t1 + p.nx + y));
+                const double *t0 = tab + (size_t)(2 * f) * W, *t1 = t0 + W;
+                double v = ea.c0[f];
+                if (ea.a[f][0] != 0.0) v = v + ea.a[f][0] * (__ldg(t0 + x) * __ldg(t0 + p.nx + y));
+                if (ea.a[f][1] != 0.0) v = v + ea.a[f][1] * (__ldg(t1 + x) * __ldg(t1 + p.nx + y));
+                e[f] = v;
             }
-            if (ea.mode == 0) error_terms(rho, ux, uy, axx, axy, ayy, tau, ea.u_max, e, acc);
-            else process_terms(rho, ux, uy, axx, ayy, ea.u_max, e, acc);
+            if constexpr (MODE == 0) error_terms(rho, ux, uy, axx, axy, ayy, half_inv_tau, den, u_max, fac, e, acc);
+            else process_terms(rho, ux, uy, axx, ayy, u_max, e, acc);
         }
-    __shared__ double sm[16][8];
-    const int lane = tid & 31, warp = tid >> 5;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        double v = acc[k];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if (lane == 0) sm[k][warp] = v;
     }
-    __syncthreads();
-    if (tid < 16) {
-        const int nw = (blockDim.x * blockDim.y + 31) >> 5;
-        double v = 0;
-        for (int w = 0; w < nw; ++w) v += sm[tid][w];
-        ea.partials[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 + tid] = v;
-    }
+    cta_partials<16>(acc, ea.partials);
 }
 
-// Second stage of the deterministic reductions: one warp per sum; lane l folds partials l, l + 32, ... in order, then a
-// fixed shuffle tree (same result on every run and every launch geometry of this stage).
-template <int NSUM>
-__device__ __forceinline__ void final_sum(const double *partials, int nblocks, double *out) {
-    const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (k >= NSUM) return;
+// Second stage of the deterministic reductions: CTA k folds sum k.  Thread t adds partials t, t + 256, ... in order, then a
+// fixed shuffle / shared-memory tree (same result on every run).
+__global__ void __launch_bounds__(256) k_final_sum(const double *__restrict__ partials, int nblocks, int nsum, double *__restrict__ out) {
+    const int k = blockIdx.x, t = threadIdx.x;
     double v = 0;
-    for (int b = lane; b < nblocks; b += 32) v += partials[(size_t)b * NSUM + k];
+    for (int b = t; b < nblocks; b += 256) v += partials[(size_t)b * nsum + k];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if (lane == 0) out[k] = v;
+    __shared__ double sm[8];
+    if ((t & 31) == 0) sm[t >> 5] = v;
+    __syncthreads();
+    if (t == 0) {
+        double r = sm[0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) r += sm[w];
+        out[k] = r;
+    }
 }
-__global__ void __launch_bounds__(512) k_errors_final(const ErrorArgs ea) { final_sum<16>(ea.partials, ea.nblocks, ea.out); }
-
-__global__ void __launch_bounds__(128) k_reduce_final(const ReduceArgs ra) { final_sum<4>(ra.partials, ra.nblocks, ra.out); }
 
 // K7: device-side initialisation.  f_i = hermite_based_equilibrium!(q, rho, u, T)
 // (velocity_distribution_function/hermite.jl:10-33) from per-node fields [ny][nx] (Float64):
@@ -1197,30 +1255,58 @@ static void launch_moments(bool pull, const KParams<T> &p, const MomentsOut &m, 
     else k_moments<T, false><<<grid, block, 0, s>>>(p, m);
 }
 template <typename T>
-static void launch_reduce(bool pull, const KParams<T> &p, const ReduceArgs &r, cudaStream_t s) {
+static void launch_snapshot(bool pull, const KParams<T> &p, double *out, cudaStream_t s) {
     dim3 block; pick_block(p.nx, block);
     dim3 grid = grid_for(p, block, p.nyl, p.nx);
-    // cap the number of partial blocks; the kernel grid-strides
-    while ((long long)grid.x * grid.y > r.nblocks && grid.y > 1) grid.y = (grid.y + 1) / 2;
-    while ((long long)grid.x * grid.y > r.nblocks && grid.x > 1) grid.x = (grid.x + 1) / 2;
+    if (pull) k_snapshot<T, true><<<grid, block, 0, s>>>(p, out);
+    else k_snapshot<T, false><<<grid, block, 0, s>>>(p, out);
+}
+// Geometry of the reducing kernels: rows per CTA such that (1) at most `cap` partials are written, (2) a thread walks up to
+// 16 rows when the grid is large (fewer, down to 1, when that would leave SMs without CTAs).
+static inline dim3 reduce_grid(int nx, int nyl, const dim3 &block, int cap, int *rows_per_cta) {
+    const long long gx = (nx + block.x - 1) / block.x, gy_nat = (nyl + block.y - 1) / block.y;
+    long long rpt = (gx * gy_nat) / (148 * 8);          // rows per thread that still leave ~8 CTAs per SM
+    rpt = rpt < 1 ? 1 : (rpt > 16 ? 16 : rpt);
+    while (gx * ((gy_nat + rpt - 1) / rpt) > cap) ++rpt;
+    *rows_per_cta = (int)(rpt * block.y);
+    return dim3((unsigned)gx, (unsigned)((gy_nat + rpt - 1) / rpt), 1);
+}
+
+template <typename T, int KIND>
+static void launch_reduce_kind(bool pull, const KParams<T> &p, const ReduceArgs &ra, const dim3 &grid, const dim3 &block, cudaStream_t s) {
+    if (pull) k_reduce<T, true, KIND><<<grid, block, 0, s>>>(p, ra);
+    else k_reduce<T, false, KIND><<<grid, block, 0, s>>>(p, ra);
+}
+template <typename T>
+static void launch_reduce(bool pull, const KParams<T> &p, const ReduceArgs &r, cudaStream_t s) {
+    dim3 block; pick_block(p.nx, block);
     ReduceArgs ra = r;
+    const dim3 grid = reduce_grid(p.nx, p.nyl, block, r.nblocks, &ra.rows_per_cta);
     ra.nblocks = grid.x * grid.y;
-    if (pull) k_reduce<T, true><<<grid, block, 0, s>>>(p, ra);
-    else k_reduce<T, false><<<grid, block, 0, s>>>(p, ra);
-    k_reduce_final<<<1, 128, 0, s>>>(ra);
+    ra.zero = 0;
+    switch (ra.kind) {
+    case LBM_REDUCE_MEAN_UX: launch_reduce_kind<T, LBM_REDUCE_MEAN_UX>(pull, p, ra, grid, block, s); break;
+    case LBM_REDUCE_VELOCITY_CHANGE: launch_reduce_kind<T, LBM_REDUCE_VELOCITY_CHANGE>(pull, p, ra, grid, block, s); break;
+    case LBM_REDUCE_DENSITY_CHANGE: launch_reduce_kind<T, LBM_REDUCE_DENSITY_CHANGE>(pull, p, ra, grid, block, s); break;
+    default: launch_reduce_kind<T, LBM_REDUCE_CONSERVED>(pull, p, ra, grid, block, s); break;
+    }
+    k_final_sum<<<4, 256, 0, s>>>(ra.partials, ra.nblocks, 4, ra.out);
 }
 
 template <typename T>
 static void launch_errors(bool pull, const KParams<T> &p, const ErrorArgs &e, cudaStream_t s) {
     dim3 block; pick_block(p.nx, block);
-    dim3 grid = grid_for(p, block, p.nyl, p.nx);
-    while ((long long)grid.x * grid.y > e.nblocks && grid.y > 1) grid.y = (grid.y + 1) / 2;
-    while ((long long)grid.x * grid.y > e.nblocks && grid.x > 1) grid.x = (grid.x + 1) / 2;
     ErrorArgs ea = e;
+    const dim3 grid = reduce_grid(p.nx, p.nyl, block, e.nblocks, &ea.rows_per_cta);
     ea.nblocks = grid.x * grid.y;
-    if (pull) k_errors<T, true><<<grid, block, 0, s>>>(p, ea);
-    else k_errors<T, false><<<grid, block, 0, s>>>(p, ea);
-    k_errors_final<<<1, 512, 0, s>>>(ea);
+    if (ea.mode == 0) {
+        if (pull) k_errors<T, true, 0><<<grid, block, 0, s>>>(p, ea);
+        else k_errors<T, false, 0><<<grid, block, 0, s>>>(p, ea);
+    } else {
+        if (pull) k_errors<T, true, 1><<<grid, block, 0, s>>>(p, ea);
+        else k_errors<T, false, 1><<<grid, block, 0, s>>>(p, ea);
+    }
+    k_final_sum<<<16, 256, 0, s>>>(ea.partials, ea.nblocks, 16, ea.out);
 }
 
 static void launch_import32(const KParams<float> &p, const double *stage, int i, cudaStream_t s) {
@@ -1261,6 +1347,7 @@ static const Ops ops = {
     &launch_import32, &launch_export32,
     &launch_init_eq<double>, &launch_init_eq<float>,
     &launch_init_analytic<double>, &launch_init_analytic<float>,
+    &launch_snapshot<double>, &launch_snapshot<float>,
     &persist_grid<double>, &persist_grid<float>,
     &launch_persist<double>, &launch_persist<float>,
     &launch_batch<double>, &launch_batch<float>,

@@ -151,7 +151,7 @@ struct lbm_ctx {
     int sep_n = 0;
     // diagnostics
     double *partials = nullptr, *red_out = nullptr, *u_old = nullptr, *rho_old = nullptr;
-    int red_blocks = 2048;
+    int red_blocks = 8192;
     // multi-GPU
     ncclComm_t comm = nullptr;
     int up = 0, down = 0;
@@ -185,6 +185,17 @@ struct lbm_ctx {
     // lbm_reduce_errors scratch: [separable tables | partials | out], kept between calls
     double *err_dev = nullptr;
     size_t err_doubles = 0;
+    std::vector<double> err_tab, scratch_row;  // host copy of the tables on the device, per (field, term) slot
+    unsigned err_tab_valid = 0;                // bit slot: err_tab[slot] is what the device holds
+    // lbm_moments output fields on the device, kept between calls
+    double *mom_dev = nullptr;
+    size_t mom_bytes = 0;
+    // asynchronous snapshots (lbm_snapshot_begin / _end)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_snap = nullptr, ev_snap_done = nullptr;
+    double *snap_dev = nullptr, *snap_host = nullptr, *snap_user = nullptr;
+    size_t snap_dev_bytes = 0, snap_host_bytes = 0;
+    bool snap_pending = false, snap_direct = false;
     // reusable device staging for the Float32 import/export conversions (grown on demand, freed by lbm_destroy)
     double *stage = nullptr;
     size_t stage_bytes = 0;
@@ -656,7 +667,11 @@ static bool persist_ok(lbm_ctx *c, long long nsteps) {
     const long long N = (long long)c->desc.nx * c->nyl;
     if (N >= (1LL << 32)) return false;
     if (c->opt_persistent == 2) {
-        if (N > PERSIST_AUTO_NODES) return false;
+        // Measured (profiles/r02): on ONE GPU graph replays of the per-step launches beat the persistent kernel at every
+        // size (128^2: 4.1 vs 9.5 us per step, 1024^2: 27.5 vs 32.2 us) -- its per-step neighbour hand-shake costs more
+        // than a kernel boundary inside a graph.  Automatic mode therefore only considers it for y-slabs, where it
+        // replaces two launches + fork/join events per step.
+        if (!p2p || N > PERSIST_AUTO_NODES) return false;
         // Float32 fast contexts on narrow lattices have the packed two-node kernel, which the persistent kernel does not
         // use: only worth it where launches dominate
         if (c->desc.dtype == LBM_F32 && c->desc.arith == LBM_ARITH_FAST && c->li.Q <= 13 && c->desc.collision != LBM_MRT &&
@@ -804,6 +819,13 @@ void lbm_destroy(lbm_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
     if (c->bstream) cudaStreamSynchronize(c->bstream);
+    if (c->snap_pending) lbm_snapshot_end(c);  // the caller's array receives its snapshot before the context goes away
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    if (c->snap_dev) cudaFree(c->snap_dev);
+    if (c->mom_dev) cudaFree(c->mom_dev);
+    if (c->snap_host) cudaFreeHost(c->snap_host);
+    for (cudaEvent_t e : {c->ev_snap, c->ev_snap_done})
+        if (e) cudaEventDestroy(e);
     drop_graphs(c);
     p2p_unmap(c);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
@@ -1043,6 +1065,77 @@ int lbm_download_f(lbm_ctx *c, double *f) {
     if (rc) return rc;
     rc = download_buffer(c, c->cur, f);
     return rc ? rc : p2p_check(c);
+}
+
+int lbm_host_alloc(void **ptr, size_t bytes) {
+    if (!ptr) return fail(LBM_ERR_INVALID, "null argument");
+    *ptr = nullptr;
+    cudaError_t e = cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(LBM_ERR_NOMEM, "cudaHostAlloc(%zu bytes): %s", bytes, cudaGetErrorString(e)); }
+    return 0;
+}
+
+int lbm_host_free(void *ptr) {
+    if (!ptr) return 0;
+    cudaError_t e = cudaFreeHost(ptr);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(LBM_ERR_CUDA, "cudaFreeHost: %s", cudaGetErrorString(e)); }
+    return 0;
+}
+
+static bool is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+int lbm_snapshot_end(lbm_ctx *c) {
+    if (!c) return fail(LBM_ERR_INVALID, "null argument");
+    if (!c->snap_pending) return 0;
+    CU(cudaSetDevice(c->desc.device));
+    c->snap_pending = false;
+    CU(cudaEventSynchronize(c->ev_snap_done));
+    if (!c->snap_direct) memcpy(c->snap_user, c->snap_host, (size_t)c->li.Q * c->nyl * c->desc.nx * 8);
+    return p2p_check(c);
+}
+
+int lbm_snapshot_begin(lbm_ctx *c, double *f) {
+    if (!c || !f) return fail(LBM_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(c->desc.device));
+    int rc = lbm_snapshot_end(c);
+    if (rc) return rc;
+    rc = wait_comm(c);
+    if (rc) return rc;
+    const size_t bytes = (size_t)c->li.Q * c->nyl * c->desc.nx * 8;
+    if (!c->copy_stream) {
+        CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&c->ev_snap, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->ev_snap_done, cudaEventDisableTiming));
+    }
+    if (c->snap_dev_bytes < bytes) {
+        if (c->snap_dev) { cudaFree(c->snap_dev); c->snap_dev = nullptr; c->snap_dev_bytes = 0; }
+        cudaError_t e = cudaMalloc(&c->snap_dev, bytes);
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(LBM_ERR_NOMEM, "cudaMalloc(%zu bytes for the snapshot buffer): %s", bytes, cudaGetErrorString(e)); }
+        c->snap_dev_bytes = bytes;
+    }
+    c->snap_direct = is_pinned(f);
+    if (!c->snap_direct && c->snap_host_bytes < bytes) {
+        if (c->snap_host) { cudaFreeHost(c->snap_host); c->snap_host = nullptr; c->snap_host_bytes = 0; }
+        cudaError_t e = cudaHostAlloc((void **)&c->snap_host, bytes, cudaHostAllocDefault);
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(LBM_ERR_NOMEM, "cudaHostAlloc(%zu bytes of snapshot staging): %s", bytes, cudaGetErrorString(e)); }
+        c->snap_host_bytes = bytes;
+    }
+    const bool pull = c->state == ST_COLLIDED;
+    if (is64(c)) c->ops->snapshot64(pull, make_params<double>(c, c->cur, c->cur), c->snap_dev, c->stream);
+    else c->ops->snapshot32(pull, make_params<float>(c, c->cur, c->cur), c->snap_dev, c->stream);
+    c->launches += 1;
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(c->ev_snap, c->stream));
+    CU(cudaStreamWaitEvent(c->copy_stream, c->ev_snap, 0));
+    CU(cudaMemcpyAsync(c->snap_direct ? f : c->snap_host, c->snap_dev, bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+    CU(cudaEventRecord(c->ev_snap_done, c->copy_stream));
+    c->snap_user = f;
+    c->snap_pending = true;
+    return 0;
 }
 
 int lbm_download_f_collision(lbm_ctx *c, double *f) {
@@ -1426,14 +1519,18 @@ int lbm_moments(lbm_ctx *c, double tau_visc, double *rho, double *ux, double *uy
     double *host[8] = {rho, ux, uy, p, p_track, sxx, sxy, syy};
     double *dev[8] = {nullptr};
     const size_t N = (size_t)c->nyl * c->desc.nx;
-    for (int k = 0; k < 8; ++k)
-        if (host[k]) {
-            cudaError_t e = cudaMalloc(&dev[k], N * 8);
-            if (e != cudaSuccess) {
-                for (int j = 0; j < k; ++j) if (dev[j]) cudaFree(dev[j]);
-                return fail(LBM_ERR_NOMEM, "cudaMalloc(%zu): %s", N * 8, cudaGetErrorString(e));
-            }
-        }
+    int nf = 0;
+    for (int k = 0; k < 8; ++k) nf += host[k] ? 1 : 0;
+    // device fields live in a per-context buffer that is kept between calls (cudaMalloc / cudaFree of 100 MB-sized blocks
+    // costs more than the kernel)
+    if (c->mom_bytes < (size_t)nf * N * 8) {
+        if (c->mom_dev) { CU(cudaStreamSynchronize(c->stream)); cudaFree(c->mom_dev); c->mom_dev = nullptr; c->mom_bytes = 0; }
+        cudaError_t e = cudaMalloc(&c->mom_dev, (size_t)nf * N * 8);
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(LBM_ERR_NOMEM, "cudaMalloc(%zu): %s", (size_t)nf * N * 8, cudaGetErrorString(e)); }
+        c->mom_bytes = (size_t)nf * N * 8;
+    }
+    for (int k = 0, j = 0; k < 8; ++k)
+        if (host[k]) dev[k] = c->mom_dev + (size_t)(j++) * N;
     MomentsOut m{dev[0], dev[1], dev[2], dev[3], dev[4], dev[5], dev[6], dev[7], tau_visc};
     const bool pull = c->state == ST_COLLIDED;
     if (is64(c)) c->ops->moments64(pull, make_params<double>(c, c->cur, c->cur), m, c->stream);
@@ -1443,7 +1540,6 @@ int lbm_moments(lbm_ctx *c, double tau_visc, double *rho, double *ux, double *uy
     for (int k = 0; k < 8 && e == cudaSuccess; ++k)
         if (host[k]) e = cudaMemcpyAsync(host[k], dev[k], N * 8, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    for (int k = 0; k < 8; ++k) if (dev[k]) cudaFree(dev[k]);
     if (e != cudaSuccess) return fail(LBM_ERR_CUDA, "lbm_moments: %s", cudaGetErrorString(e));
     return p2p_check(c);
 }
@@ -1462,29 +1558,43 @@ static int reduce_errors_mode(lbm_ctx *c, int mode, double tau_visc, double u_ma
     int rc = wait_comm(c);
     if (rc) return rc;
     const int nx = c->desc.nx, nyl = c->nyl, W = nx + nyl;
-    std::vector<double> tab((size_t)16 * W, 1.0);
-    ErrorArgs ea;
-    memset(&ea, 0, sizeof(ea));
-    for (int f = 0; f < 8; ++f) {
-        ea.c0[f] = expected[f].c0;
-        for (int k = 0; k < 2; ++k) {
-            ea.a[f][k] = expected[f].a[k];
-            double *t = tab.data() + (size_t)(2 * f + k) * W;
-            if (expected[f].x[k]) memcpy(t, expected[f].x[k], (size_t)nx * 8);
-            if (expected[f].y[k]) memcpy(t + nx, expected[f].y[k], (size_t)nyl * 8);
-        }
-    }
-    const int nblocks = 1024;
-    const size_t need = tab.size() + (size_t)nblocks * 16 + 16;
+    const size_t tabn = (size_t)16 * W;
+    const int nblocks = 8192;
+    const size_t need = tabn + (size_t)nblocks * 16 + 16;
     if (c->err_doubles < need) {
         if (c->err_dev) { CU(cudaStreamSynchronize(c->stream)); cudaFree(c->err_dev); c->err_dev = nullptr; c->err_doubles = 0; }
         CU(cudaMalloc(&c->err_dev, need * 8));
         c->err_doubles = need;
+        c->err_tab.clear();
     }
     double *dev = c->err_dev;
-    cudaError_t e = cudaMemcpyAsync(dev, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, c->stream);
+    // Separable tables: a host copy of what the device holds is kept per (field, term) slot, and only slots whose
+    // contents changed are uploaded -- between two calls of a run usually none (the time dependence of the analytic
+    // fields sits in the coefficients), so the call is the two kernels plus a 128-byte read-back.  Slots of terms with a
+    // zero coefficient are never read by the kernel and are skipped.
+    if (c->err_tab.size() != tabn) { c->err_tab.assign(tabn, 0.0); c->err_tab_valid = 0; }
+    ErrorArgs ea;
+    memset(&ea, 0, sizeof(ea));
+    cudaError_t e = cudaSuccess;
+    for (int f = 0; f < 8; ++f) {
+        ea.c0[f] = expected[f].c0;
+        for (int k = 0; k < 2; ++k) {
+            ea.a[f][k] = expected[f].a[k];
+            if (expected[f].a[k] == 0.0) continue;
+            const int slot = 2 * f + k;
+            c->scratch_row.assign((size_t)W, 1.0);
+            if (expected[f].x[k]) memcpy(c->scratch_row.data(), expected[f].x[k], (size_t)nx * 8);
+            if (expected[f].y[k]) memcpy(c->scratch_row.data() + nx, expected[f].y[k], (size_t)nyl * 8);
+            double *t = c->err_tab.data() + (size_t)slot * W;
+            if (((c->err_tab_valid >> slot) & 1u) && memcmp(t, c->scratch_row.data(), (size_t)W * 8) == 0) continue;
+            // (no launch is reading the device slot: every call of this function ends with a stream synchronise)
+            memcpy(t, c->scratch_row.data(), (size_t)W * 8);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(dev + (size_t)slot * W, t, (size_t)W * 8, cudaMemcpyHostToDevice, c->stream);
+            c->err_tab_valid |= 1u << slot;
+        }
+    }
     ea.tab = dev;
-    ea.partials = dev + tab.size();
+    ea.partials = dev + tabn;
     ea.out = ea.partials + (size_t)nblocks * 16;
     ea.nblocks = nblocks;
     ea.tau_visc = tau_visc;
@@ -1520,7 +1630,7 @@ int lbm_reduce(lbm_ctx *c, int32_t kind, double *out, int32_t n) {
         CU(cudaMalloc(&c->rho_old, N * 8));
         CU(cudaMemsetAsync(c->rho_old, 0, N * 8, c->stream));  // zeros(nx, ny), process_iterative_initialization.jl:9-10
     }
-    ReduceArgs ra{kind, c->partials, kind == LBM_REDUCE_DENSITY_CHANGE ? c->rho_old : c->u_old, c->red_out, c->red_blocks};
+    ReduceArgs ra{kind, c->partials, kind == LBM_REDUCE_DENSITY_CHANGE ? c->rho_old : c->u_old, c->red_out, c->red_blocks, 0, 0};
     const bool pull = c->state == ST_COLLIDED;
     if (is64(c)) c->ops->reduce64(pull, make_params<double>(c, c->cur, c->cur), ra, c->stream);
     else c->ops->reduce32(pull, make_params<float>(c, c->cur, c->cur), ra, c->stream);

@@ -284,6 +284,21 @@ function next!(pm::TrackHydrodynamicErrors, m::B200Model, t::Int64)
     should_stop
 end
 
+# TakeSnapshots.next! (take_snapshots.jl:12-29): push!(snapshots, copy(f_in)) becomes an asynchronous device-to-host copy
+# (lbm_snapshot_begin): the array is pushed right away and filled while the next steps run; the copy is waited for when
+# the next snapshot is taken and at the end of simulate (finish_snapshots!).
+host_visible(pm::TakeSnapshots, t) = pm.every_t isa Int ? mod(t, pm.every_t) == 0 : t in pm.every_t
+finish_snapshots!(m::B200Model) = check(ccall((:lbm_snapshot_end, LIB), Cint, (Ptr{Cvoid},), m.ctx))
+function next!(pm::TakeSnapshots, m::B200Model, t::Int64)
+    host_visible(pm, t) || return false
+    finish_snapshots!(m)
+    f = Array{Float64}(undef, m.nx, m.ny, length(m.quadrature.weights))
+    push!(pm.snapshots, f)          # the vector keeps the array alive while the copy is in flight
+    push!(pm.timesteps, t)
+    check(ccall((:lbm_snapshot_begin, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), m.ctx, f))
+    false
+end
+
 # CompareWithAnalyticalSolution.next! / process! (processing_methods.jl:100-262): the 12 sums of process! come from one
 # device reduction (lbm_reduce_process); rho, u, p of the problem are passed in separable form like the error norms.
 host_visible(pm::CompareWithAnalyticalSolution, t) =
@@ -348,10 +363,11 @@ function simulate(m::B200Model, time)
         host_visible(pm, t + 1) || continue
         step!(m, t0, n, Δt)
         t0, n = t + 1, 0
-        next!(m, t + 1) && return m
+        next!(m, t + 1) && (finish_snapshots!(m); return m)
     end
     n > 0 && step!(m, t0, n, Δt)
     next!(m, last(time) + 1)
+    finish_snapshots!(m)
     m
 end
 

@@ -38,7 +38,7 @@ EXPORTS = [
     "lbm_collide", "lbm_stream", "lbm_apply_bcs", "lbm_step", "lbm_sync", "lbm_moments", "lbm_reduce",
     "lbm_reduce_errors", "lbm_reduce_process",
     "lbm_kernel_launches", "lbm_halo_path", "lbm_last_step_ms", "lbm_timer_start", "lbm_timer_stop", "lbm_set_option",
-    "lbm_init_analytic",
+    "lbm_init_analytic", "lbm_host_alloc", "lbm_host_free", "lbm_snapshot_begin", "lbm_snapshot_end",
     "lbm_batch_create", "lbm_batch_destroy", "lbm_batch_set_tau", "lbm_batch_set_force_uniform", "lbm_batch_upload_f",
     "lbm_batch_broadcast_f", "lbm_batch_download_f", "lbm_batch_run", "lbm_batch_status", "lbm_batch_reduce_errors",
     "lbm_batch_last_run_ms", "lbm_batch_kernel_launches",
@@ -135,6 +135,10 @@ def lib():
     l.lbm_timer_start.argtypes = [vp]
     l.lbm_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
     l.lbm_init_analytic.argtypes = [vp, C.POINTER(lbm_init_spec)]
+    l.lbm_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
+    l.lbm_host_free.argtypes = [vp]
+    l.lbm_snapshot_begin.argtypes = [vp, vp]
+    l.lbm_snapshot_end.argtypes = [vp]
     l.lbm_batch_create.argtypes = [C.POINTER(lbm_desc), C.c_int32, C.POINTER(vp)]
     l.lbm_batch_destroy.argtypes = [vp]
     l.lbm_batch_destroy.restype = None
@@ -269,6 +273,20 @@ class Context:
         out = self.new_f() if out is None else self._check_f(out, True)
         check(lib().lbm_download_f(self._h, out.ctypes.data))
         return out
+
+    def snapshot_begin(self, out=None):
+        """TakeSnapshots: start an asynchronous copy of f_stream of the current state (take_snapshots.jl:12-29) and return
+        the array it will land in -- page-locked unless `out` is given.  Valid after snapshot_end(); steps enqueued in
+        between run concurrently with the copy and the fused state machine is not disturbed."""
+        out = pinned_empty(self.shape) if out is None else self._check_f(out, True)
+        check(lib().lbm_snapshot_begin(self._h, out.ctypes.data))
+        self._snapshot_out = out
+        return out
+
+    def snapshot_end(self):
+        if getattr(self, "_h", None):  # lbm_destroy completes a pending snapshot: nothing left to wait for afterwards
+            check(lib().lbm_snapshot_end(self._h))
+        self._snapshot_out = None
 
     def upload_f_rows(self, y0, f_rows):
         """f_rows: (NX, ny, Q) Fortran-ordered block for local rows y0 .. y0+ny-1."""
@@ -412,6 +430,17 @@ class Context:
 
     def set_option(self, key, value):
         check(lib().lbm_set_option(self._h, key.encode(), int(value)))
+
+
+def pinned_empty(shape):
+    """np.empty(shape, float64, order="F") in page-locked host memory (lbm_host_alloc); freed with the array."""
+    import weakref
+    n = int(np.prod(shape))
+    p = C.c_void_p()
+    check(lib().lbm_host_alloc(C.byref(p), n * 8))
+    buf = (C.c_double * max(n, 1)).from_address(p.value)
+    weakref.finalize(buf, lib().lbm_host_free, p.value)
+    return np.frombuffer(buf, dtype=np.float64, count=n).reshape(shape, order="F")
 
 
 def _sep_fields(expected, nx, ny):

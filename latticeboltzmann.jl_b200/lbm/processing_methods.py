@@ -305,23 +305,42 @@ def _process_separable(pr, q, time, state):
 
 
 class TakeSnapshots(ProcessingMethodBase):
-    """take_snapshots.jl:3-29: snapshot = copy(f_in) -> a device-to-host download."""
+    """take_snapshots.jl:3-29: snapshot = copy(f_in).  On the device that is one kernel writing f_stream of the current
+    state into a compact buffer plus a device-to-host copy on a copy stream (lbm_snapshot_begin); the copy of snapshot k
+    is only waited for when snapshot k+1 is taken or `snapshots` is read, so the step loop never stalls on PCIe."""
 
     def __init__(self, problem, every_t):
         self.problem = problem
         self.every_t = every_t
-        self.snapshots = []
+        self._snapshots = []
         self.timesteps = []
+        self._pending = None
 
     def noop(self, t):
         if isinstance(self.every_t, int):
             return t % self.every_t != 0
         return t not in self.every_t
 
+    def flush(self):
+        if self._pending is not None:
+            self._pending.snapshot_end()
+            self._pending = None
+
+    @property
+    def snapshots(self):
+        self.flush()
+        return self._snapshots
+
     def next_(self, q, state, t):
         if self.noop(t):
             return False
-        self.snapshots.append(state.download_f())
+        self.flush()
+        ctx = state.ctx
+        if hasattr(ctx, "snapshot_begin"):
+            self._snapshots.append(ctx.snapshot_begin())
+            self._pending = ctx
+        else:
+            self._snapshots.append(state.download_f())
         self.timesteps.append(t)
         return False
 

@@ -773,6 +773,44 @@ def test_couette_moving_wall_steady_state(oracle, name):
     model.close()
 
 
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_asynchronous_snapshots_do_not_disturb_the_run(oracle, dtype):
+    """lbm_snapshot_begin / _end (TakeSnapshots, take_snapshots.jl:12-29): every snapshot equals the oracle's f_stream at
+    that step, the copy overlaps the following steps, and the final state equals the one of a run that took no snapshots
+    (the snapshot kernel reads the post-collision state through the pull, it does not materialise f_stream)."""
+    O = oracle
+    q, qo = lbm.D2Q13(), O.L.D2Q13()
+    nx, ny = 96, 40
+    ph, po = lbm.CouetteFlow.fields(1.0, 0.01, 1 / 6, nx, ny, (1.0, 1.0)), O.CouetteFlow(1 / 6, NX=nx, NY=ny, u_max=0.01, convenience=False)
+    f0 = O.initialize("ZeroVelocityInitialCondition", qo, po)
+    cmo = O.collision_model("TRT", qo, po)
+    want, f = {}, f0
+    for t in range(1, 31):
+        f, _ = O.step(cmo, qo, po.boundary_conditions(), f)
+        want[t] = f
+    tol = 0 if dtype == "f64" else 1e-6
+    m = lbm.LatticeBoltzmannModel(ph, q, collision_model=lbm.TRT, initialization_strategy=lbm.ZeroVelocityInitialCondition(), dtype=dtype)
+    ctx = m.ctx
+    ctx.step(0, 7)
+    l0 = ctx.kernel_launches
+    a = ctx.snapshot_begin()                      # page-locked array from the library
+    assert ctx.kernel_launches == l0 + 1           # one kernel, no materialisation
+    ctx.step(7, 13)                                # enqueued while the copy is in flight
+    ctx.snapshot_end()
+    assert np.abs(to_oracle_layout(a) - want[7]).max() <= tol
+    b = ctx.new_f()                                # pageable array of the caller: staged through the library's buffer
+    ctx.snapshot_begin(b)
+    c = ctx.snapshot_begin()                       # a second begin completes the first
+    assert np.abs(to_oracle_layout(b) - want[20]).max() <= tol
+    ctx.step(20, 10)
+    ctx.snapshot_end()
+    assert np.array_equal(b, c)
+    got = to_oracle_layout(ctx.download_f())
+    assert np.abs(got - want[30]).max() <= tol
+    m.close()
+    assert np.abs(to_oracle_layout(a) - want[7]).max() <= tol  # page-locked arrays outlive the context
+
+
 @pytest.mark.parametrize("kind", ["LinearizedThermalDiffusion", "LinearizedTransverseShearWave"])
 @pytest.mark.parametrize("name,model", [("D2Q9", "SRT"), ("D2Q9", "MRT"), ("D2Q17", "TRT"), ("D2Q37", "MRT")])
 def test_linearized_hydrodynamic_modes(oracle, kind, name, model):
@@ -795,7 +833,9 @@ def test_linearized_hydrodynamic_modes(oracle, kind, name, model):
     assert len(pm.df) == len(mo.pm.df)
     for got, want in zip(pm.df, mo.pm.df):
         for k in want:
-            assert abs(got[k] - want[k]) <= 1e-10 * abs(want[k]) + 1e-15, (kind, name, model, k, got[k], want[k])
+            # sums that vanish analytically (the momentum of a standing wave) are round-off on either side: O(1e-12) of
+            # the O(100) total density
+            assert abs(got[k] - want[k]) <= 1e-10 * abs(want[k]) + 1e-10, (kind, name, model, k, got[k], want[k])
     m.close()
     # Float32 storage: populations within 1e-5 of the oracle
     m = lbm.LatticeBoltzmannModel(ph, q, collision_model=cm, process_method=lbm.ProcessingMethod(ph, False, n_steps), dtype="f32")
@@ -824,7 +864,7 @@ def test_process_sums_on_device_match_oracle(oracle, name, dtype):
         mo = O.make_model(po, qo, "TRT", strategy="ZeroVelocityInitialCondition",
                           pm=O.CompareWithAnalyticalSolution(po, True, n_steps, O.NoStoppingCriteria()))
         O.simulate_model(mo, range(0, n_steps + 1))
-        assert len(pm.df) == len(mo.pm.df) == n_steps + 1
+        assert len(pm.df) == len(mo.pm.df) == n_steps + 2  # one row per loop pass + the final next!(last(time) + 1)
         tol = 1e-10 if dtype == "f64" else 2e-5
         for got, want in zip(pm.df, mo.pm.df):
             for k in want:
