@@ -61,9 +61,12 @@ def parse():
                     help="BASELINE.json config preset (C2 = default bench workload; see build_case)")
     ap.add_argument("--p2p", type=int, default=1, help="N > 1: 1 = peer-memory halo stores (default), 0 = NCCL send/recv")
     ap.add_argument("--graph", type=int, default=1, help="1 = replay CUDA graphs of 16 fused steps (default), 0 = plain launches")
+    ap.add_argument("--persistent", type=int, default=2, help="0 = launches per step (graphs), 1 = persistent multi-step kernel wherever possible, 2 = automatic")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the post-timing multi-slab parity check against the oracle")
+    ap.add_argument("--no-also", action="store_true", help="skip the strong-scaling configs reported under `also` (C5s, C3, C4)")
+    ap.add_argument("--also-shrink", type=int, default=1, help="divide the grids of the `also` configs by this (tests)")
     ap.add_argument("--cpu-n", type=int, default=4096, help="CPU arm grid (default: the full 4096 x 4096 workload grid)")
     ap.add_argument("--cpu-steps", type=int, default=40, help="lattice steps of the cpu_baseline sample (reference arm: a tenth per bench step)")
     return ap.parse_args()
@@ -215,7 +218,7 @@ def build_case(a, world, lbm):
         elif a.config == "C5w":
             nx, ny, scaling = 16384, 16384 * world, "weak"
         else:
-            nx, ny, scaling = 32768, 32768, "strong"
+            nx, ny, scaling = 32768 // a.also_shrink, 32768 // a.also_shrink, "strong"
         problem = lbm.TGV(q, 0.8, max(nx // 16, 1), nx, ny)
         cm = lbm.CollisionModel(CMs[a.collision], q, problem)
         name = f"{a.lattice} {a.collision} Taylor-Green vortex decay, periodic (BASELINE configs[{1 if a.config == 'C2' else 4}])"
@@ -224,7 +227,7 @@ def build_case(a, world, lbm):
     if a.config == "C3":
         # D2Q9 SRT + uniform force Poiseuille channel 1024 x 8192, bounce-back North + South (strong scaling)
         q = lbm.D2Q9()
-        nx, ny = 1024, 8192
+        nx, ny = 1024, 8192 // a.also_shrink
         problem = lbm.PoiseuilleFlow.fields(1.0, 0.1 / (ny / 5), 1 / 6, nx, ny, 1.0, (1.0, 1.0), 1.0)
         cm = lbm.CollisionModel(lbm.SRT, q, problem)
         return dict(q=q, problem=problem, cm=cm, nx=nx, ny=ny, scaling="strong",
@@ -232,7 +235,7 @@ def build_case(a, world, lbm):
                     workload="D2Q9 SRT+force Poiseuille, bounce-back walls, 1024x8192 (BASELINE configs[2])")
     # C4: D2Q37 TRT Couette 8192^2, bounce-back South + moving wall North, halo width 3 (strong scaling)
     q = lbm.D2Q37()
-    nx = ny = 8192
+    nx = ny = 8192 // a.also_shrink
     problem = lbm.CouetteFlow.fields(1.0, 0.01 / (ny / 5), 0.3 / q.speed_of_sound_squared, nx, ny, (1.0, 1.0))
     cm = lbm.CollisionModel(lbm.TRT, q, problem)
     return dict(q=q, problem=problem, cm=cm, nx=nx, ny=ny, scaling="strong", init=lbm.ZeroVelocityInitialCondition(),
@@ -248,7 +251,7 @@ def parity_check(world, rank, local, comm, lbm, torch, dist):
     q = lbm.D2Q9()
     problem = lbm.TGV(q, 0.8, nx // 16, nx, ny)
     cm = lbm.CollisionModel(lbm.TRT, q, problem)
-    cases, want, f0_full = [], None, None
+    cases, want, f0_full, f0_gathered = [], None, None, False
     for dtype, arith in (("f64", "exact"), ("f32", "fast")):
         for p2p in ((1, 0) if world > 1 else (1,)):
             ctx = lbm.model.make_context(q, cm, problem.boundary_conditions(), nx, ny, dtype, arith, comm, local)
@@ -269,8 +272,8 @@ def parity_check(world, rank, local, comm, lbm, torch, dist):
                 dist.gather(t, parts, dst=0)
                 return np.concatenate([x.cpu().numpy() for x in parts], axis=1) if rank == 0 else None
             got_full = gather(got)
-            if f0_full is None:
-                f0_full = gather(f0)
+            if not f0_gathered:  # a collective: every rank must take this branch the same number of times
+                f0_full, f0_gathered = gather(f0), True
             if rank == 0:
                 if want is None:
                     import oracle.lbm_oracle as O
@@ -290,6 +293,99 @@ def parity_check(world, rank, local, comm, lbm, torch, dist):
             "halo_paths": {"0": "single GPU", "1": "NCCL send/recv", "2": "peer-memory stores"}, "cases": cases, "ok": ok,
             "max_rel_err": max(c["max_rel_err"] for c in cases),
             "bit_identical": all(c["bit_identical"] for c in cases if c["dtype"] == "f64")}
+
+
+ALSO_PRESETS = (("C5s", 10), ("C3", 100), ("C4", 20))  # preset, lattice steps per timed batch
+ALSO_FILE = os.path.join(ROOT, ".bench_also_n1.json")  # N = 1 figures of the same scaling run (efficiency denominator)
+
+
+def also_cases(a, world, rank, local, comm, lbm, torch, dist, peak):
+    """OUTSIDE the headline's timed region: the north_star's STRONG-scaling configurations on the same N ranks -- C5s (D2Q9
+    TRT TGV 32768^2), C3 (D2Q9 SRT + force Poiseuille 1024 x 8192, walls) and C4 (D2Q37 TRT Couette 8192^2, halo 3) -- a
+    few device batches each, timed like the headline (CUDA events on the library's stream, max over ranks).  An N = 1 run
+    leaves its figures in .bench_also_n1.json; later runs with N > 1 on the same box report their efficiency against
+    them (value_N / (N value_1))."""
+    import argparse
+    n1 = {}
+    if world > 1 and a.also_shrink == 1 and os.path.exists(ALSO_FILE) and time.time() - os.path.getmtime(ALSO_FILE) < 6 * 3600:
+        try:
+            n1 = json.load(open(ALSO_FILE))
+        except Exception:
+            n1 = {}
+    out = []
+    for preset, inner in ALSO_PRESETS:
+        b = argparse.Namespace(**vars(a))
+        b.config, b.dtype, b.arith = preset, "f64", a.arith
+        entry = {"preset": preset, "scaling": "strong"}
+        ctx = None
+        try:
+            case = build_case(b, world, lbm)
+            q, problem, cm, nx, ny = case["q"], case["problem"], case["cm"], case["nx"], case["ny"]
+            entry.update(workload=case["workload"], grid_global=[nx, ny], lattice_steps_per_batch=inner)
+            need = 2 * nx * (ny // world + 8) * q.Q * 8
+            free = torch.cuda.mem_get_info()[0]
+            fits = need <= free - (2 << 30)
+            if world > 1:  # lbm_create is collective: every rank takes the same decision
+                tt = torch.tensor([1.0 if fits else 0.0], dtype=torch.float64, device="cuda")
+                dist.all_reduce(tt, op=dist.ReduceOp.MIN)
+                fits = bool(tt.cpu()[0] > 0.5)
+            if not fits:
+                raise MemoryError(f"needs {need / 1e9:.1f} GB per GPU, {free / 1e9:.1f} GB free on rank {rank}")
+            ctx = lbm.model.make_context(q, cm, problem.boundary_conditions(), nx, ny, "f64", a.arith, comm, local)
+            ctx.set_option("p2p", a.p2p)
+            ctx.set_option("graph", a.graph)
+            ctx.set_option("persistent", a.persistent)
+            state = lbm.DeviceState(ctx, q, cm, comm)
+            state.prepare_force(0, 1, problem.delta_t())
+            t0 = time.perf_counter()
+            if not lbm.initialize_on_device(case["init"], q, problem, ctx):
+                raise RuntimeError("device-side initialisation unavailable")
+            ctx.sync()
+            entry["init_on_device_s"] = round(time.perf_counter() - t0, 4)
+            t = 0
+            for _ in range(3):
+                ctx.step(t, inner, 1.0)
+                t += inner
+            ctx.sync()
+            if world > 1:
+                dist.barrier()
+            nb = 5
+            l0 = ctx.kernel_launches
+            ctx.timer_start()
+            for _ in range(nb):
+                ctx.step(t, inner, 1.0)
+                t += inner
+            dev_ms = ctx.timer_stop()
+            launches = ctx.kernel_launches - l0
+            from lbm import _abi
+            cons = ctx.reduce(_abi.REDUCE_CONSERVED)
+            if world > 1:
+                tt = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                dev_ms = float(tt.cpu()[0])
+            value = nx * ny * inner * nb / (dev_ms * 1e-3) / 1e6
+            gbs = value * 1e6 * 2 * q.Q * 8 / 1e9 / world
+            entry.update(value=value, unit="MLUPS", ms_per_lattice_step=dev_ms / (nb * inner), gbs_per_gpu=gbs,
+                         frac_of_hbm_peak_per_gpu=gbs / peak, grid_per_gpu=[nx, ctx.ny_local], halo_path=ctx.halo_path,
+                         launches_per_lattice_step=launches / (nb * inner), finite=bool(np.isfinite(cons).all()))
+            if world == 1:
+                n1[preset] = value
+            elif preset in n1:
+                entry.update(n1_value=n1[preset], efficiency_vs_n1=value / (world * n1[preset]))
+        except Exception as e:  # a configuration that does not fit or fails is reported, it never takes the headline down
+            entry["skipped"] = f"{type(e).__name__}: {e}"[:300]
+        finally:
+            if ctx is not None:
+                ctx.close()
+        if world > 1:
+            dist.barrier()
+        out.append(entry)
+    if world == 1 and rank == 0 and n1 and a.also_shrink == 1:
+        try:
+            json.dump(n1, open(ALSO_FILE, "w"))
+        except OSError:
+            pass
+    return out
 
 
 def measured_peak():
@@ -333,6 +429,7 @@ def run_b200(a):
     ctx.set_option("variant", a.variant)
     ctx.set_option("p2p", a.p2p)
     ctx.set_option("graph", a.graph)
+    ctx.set_option("persistent", a.persistent)
     halo_path = {0: "none (single GPU)", 1: "NCCL send/recv on a side stream", 2: "peer-memory stores from the boundary-row launch"}[ctx.halo_path]
     nyl = ctx.ny_local
     state = lbm.DeviceState(ctx, q, cm, comm)
@@ -427,6 +524,8 @@ def run_b200(a):
                          f"(oracle/lbm_oracle.c) with OpenMP over rows"}
     ctx.close()
     parity = None if a.no_parity else parity_check(world, rank, local, comm, lbm, torch, dist)
+    headline = a.config == "C2" and ((a.nx, a.ny) == (4096, 4096) or a.also_shrink > 1)
+    also = None if (a.no_also or not headline) else also_cases(a, world, rank, local, comm, lbm, torch, dist, peak)
     if scaling == "weak":
         cfg = config_keys(case["workload"], a.config, [nx, ny // world], world, inner, a.arith, a.dtype, q.Q, "weak")
     else:
@@ -438,7 +537,7 @@ def run_b200(a):
             "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": a.dtype, "data": "synthetic",
             "config": cfg,
-            "details": {"grid_local": [nx, nyl], "variant": a.variant, "cuda_graphs": bool(a.graph), "halo_exchange": halo_path,
+            "details": {"grid_local": [nx, nyl], "variant": a.variant, "cuda_graphs": bool(a.graph), "persistent": a.persistent, "halo_exchange": halo_path,
                         "wall_ms_per_step": region_ms / a.steps},
             "clocks": clocks,
             "e2e": e2e,
@@ -448,6 +547,7 @@ def run_b200(a):
                          "kernel_ms": kern_ms, "kernel": "k_step<%s, %s, pull>" % (type(cm).__name__, a.dtype)},
             "cpu_baseline": cpu,
             "parity_check": parity,
+            "also": also,
         }))
     if world > 1:
         dist.destroy_process_group()

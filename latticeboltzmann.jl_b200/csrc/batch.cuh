@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(256) k_batch_errors(const __grid_constant__ Ba
             const double *t0 = ea.tab + (size_t)(2 * fi) * W, *t1 = t0 + W;
             e[fi] = cf[3 * fi] + cf[3 * fi + 1] * (__ldg(t0 + x) * __ldg(t0 + ea.nx + y)) + cf[3 * fi + 2] * (__ldg(t1 + x) * __ldg(t1 + ea.nx + y));
         }
-        error_terms(rho, ux, uy, axx, axy, ayy, half_inv_tau, den, u_max, fac, e, acc);
+        error_terms<true>(rho, ux, uy, axx, axy, ayy, half_inv_tau, den, u_max, fac, e, acc);
     }
 #pragma unroll
     for (int j = 0; j < 16; ++j) sm[w][j][lane] = acc[j];

@@ -729,9 +729,24 @@ __device__ __forceinline__ void fields_of(const T (&f)[Q], double &rho, double &
         if constexpr (Shifted<T>::value) g[i] = (double)f[i] + c_lat64.w[i];
         else g[i] = (double)f[i];
     });
+    const LatConst<double> &c = c_lat64;
+#if LBM_FAST
+    {   // density = sum(f), velocity! = sum(f c) / rho (moments.jl:3-19) with ONE reciprocal instead of two divisions
+        rho = g[0];
+        static_for<1, Q>([&](auto I) { rho = rho + g[decltype(I)::value]; });
+        double jx = 0, jy = 0;
+        static_for<0, Q>([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            if constexpr (L::cx(i) != 0) jx = jx + cmul<L::cx(i)>(g[i]);
+            if constexpr (L::cy(i) != 0) jy = jy + cmul<L::cy(i)>(g[i]);
+        });
+        const double inv = 1.0 / rho;
+        ux = jx * inv; uy = jy * inv;
+    }
+#else
     double drho_unused;
     rho_u<double>(g, rho, ux, uy, drho_unused);
-    const LatConst<double> &c = c_lat64;
+#endif
     axx = g[0] * c.H2[0][0]; axy = g[0] * c.H2[0][1]; ayy = g[0] * c.H2[0][2];
     static_for<1, Q>([&](auto I) {
         constexpr int i = decltype(I)::value;
@@ -892,6 +907,7 @@ struct InvConst {
 // One node's contribution to the 16 sums of TrackHydrodynamicErrors.next! (track_hydrodynamic_errors.jl:134-203):
 // rho, u, p = tr(P)/D, sigma as in k_moments, scaled to dimensionless units, against the expected fields e[8] =
 // rho, ux, uy, p, sxx, sxy, syx, syy.
+template <bool EXPECTED_SQUARES>
 __device__ __forceinline__ void error_terms(double rho, double ux, double uy, double axx, double axy, double ayy, double half_inv_tau,
                                             const InvConst &den, const InvConst &u_max, double fac, const double (&e)[8],
                                             double (&acc)[16]) {
@@ -904,13 +920,16 @@ __device__ __forceinline__ void error_terms(double rho, double ux, double uy, do
     const double vx = u_max.div(ux), vy = u_max.div(uy);
     acc[0] += (rho - e[0]) * (rho - e[0]);
     acc[1] += (vx - e[1]) * (vx - e[1]) + (vy - e[2]) * (vy - e[2]);
-    acc[2] += e[1] * e[1] + e[2] * e[2];
     acc[3] += (pr - e[3]) * (pr - e[3]);
-    acc[4] += e[3] * e[3];
-    acc[5] += (e[4] - sxx) * (e[4] - sxx); acc[6] += e[4] * e[4];
-    acc[7] += (e[5] - sxy) * (e[5] - sxy); acc[8] += e[5] * e[5];
-    acc[9] += (e[7] - syy) * (e[7] - syy); acc[10] += e[7] * e[7];
-    acc[11] += (e[6] - sxy) * (e[6] - sxy); acc[12] += e[6] * e[6];
+    acc[5] += (e[4] - sxx) * (e[4] - sxx);
+    acc[7] += (e[5] - sxy) * (e[5] - sxy);
+    acc[9] += (e[7] - syy) * (e[7] - syy);
+    acc[11] += (e[6] - sxy) * (e[6] - sxy);
+    if constexpr (EXPECTED_SQUARES) {  // sums of the expected fields alone: separable, so the large-grid path leaves them to the host
+        acc[2] += e[1] * e[1] + e[2] * e[2];
+        acc[4] += e[3] * e[3];
+        acc[6] += e[4] * e[4]; acc[8] += e[5] * e[5]; acc[10] += e[7] * e[7]; acc[12] += e[6] * e[6];
+    }
     acc[13] += rho; acc[14] += rho * (vx + vy); acc[15] += rho * (vx * vx + vy * vy);
 }
 
@@ -941,32 +960,37 @@ __device__ __forceinline__ void process_terms(double rho, double ux, double uy, 
 // MODE 0: those sums, MODE 1: the sums of process!.  Terms whose coefficient is zero (most fields of most problems have
 // one term or none) are skipped by a launch-uniform branch, so their tables are never read.
 template <typename T, bool PULL, int MODE>
-__global__ void __launch_bounds__(256, 2) k_errors(const __grid_constant__ KParams<T> p, const __grid_constant__ ErrorArgs ea) {
+__global__ void __launch_bounds__(256, 3) k_errors(const __grid_constant__ KParams<T> p, const __grid_constant__ ErrorArgs ea) {
     double acc[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) acc[k] = 0;
-    const int W = p.nx + p.nyl;
+    const unsigned W = (unsigned)(p.nx + p.nyl);
     const double half_inv_tau = 1 / (2 * ea.tau_visc);
     const InvConst den(1 + 1 / (2 * ea.tau_visc)), u_max(ea.u_max);
     const double fac = 1 / (ea.u_max * ea.u_max);
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y0 = blockIdx.y * ea.rows_per_cta, y1 = min(p.nyl, y0 + ea.rows_per_cta);
+    const unsigned mask = ea.mask;
     if (x < p.nx) {
-        const double *__restrict__ tab = ea.tab;
-#pragma unroll 2
+        // slot s = 2 f + k of the tables: X_s at tab[s W + x], Y_s at tab[s W + nx + y]; 32-bit offsets from two bases
+        const double *__restrict__ tx = ea.tab + x;
+#pragma unroll 1
         for (int y = y0 + threadIdx.y; y < y1; y += blockDim.y) {
             double rho, ux, uy, axx, axy, ayy;
             node_fields<T, PULL>(p, x, y, rho, ux, uy, axx, axy, ayy);
+            const double *__restrict__ ty = ea.tab + (p.nx + y);
             double e[8];
 #pragma unroll
             for (int f = 0; f < 8; ++f) {
-                const double *t0 = tab + (size_t)(2 * f) * W, *t1 = t0 + W;
                 double v = ea.c0[f];
-                if (ea.a[f][0] != 0.0) v = v + ea.a[f][0] * (__ldg(t0 + x) * __ldg(t0 + p.nx + y));
-                if (ea.a[f][1] != 0.0) v = v + ea.a[f][1] * (__ldg(t1 + x) * __ldg(t1 + p.nx + y));
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const unsigned s = 2 * f + k;
+                    if (mask & (1u << s)) v = v + ea.a[f][k] * (__ldg(tx + s * W) * __ldg(ty + s * W));
+                }
                 e[f] = v;
             }
-            if constexpr (MODE == 0) error_terms(rho, ux, uy, axx, axy, ayy, half_inv_tau, den, u_max, fac, e, acc);
+            if constexpr (MODE == 0) error_terms<false>(rho, ux, uy, axx, axy, ayy, half_inv_tau, den, u_max, fac, e, acc);
             else process_terms(rho, ux, uy, axx, ayy, u_max, e, acc);
         }
     }
@@ -1299,6 +1323,10 @@ static void launch_errors(bool pull, const KParams<T> &p, const ErrorArgs &e, cu
     ErrorArgs ea = e;
     const dim3 grid = reduce_grid(p.nx, p.nyl, block, e.nblocks, &ea.rows_per_cta);
     ea.nblocks = grid.x * grid.y;
+    ea.mask = 0;
+    for (int f = 0; f < 8; ++f)
+        for (int k = 0; k < 2; ++k)
+            if (ea.a[f][k] != 0.0) ea.mask |= 1u << (2 * f + k);
     if (ea.mode == 0) {
         if (pull) k_errors<T, true, 0><<<grid, block, 0, s>>>(p, ea);
         else k_errors<T, false, 0><<<grid, block, 0, s>>>(p, ea);

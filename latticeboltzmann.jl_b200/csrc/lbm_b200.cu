@@ -175,7 +175,7 @@ struct lbm_ctx {
     bool timed = false;
     int opt_variant = 0;
     int opt_overlap = 1;
-    // persistent multi-step kernel (persist.cuh): 0 = off, 1 = whenever possible, 2 = automatic (launch-bound slabs)
+    // persistent multi-step kernel (persist.cuh): 0 = off, 1 = whenever possible, 2 = automatic (= off: measured slower, see persist_ok)
     int opt_persistent = 2;
     int pg_ctas[2] = {-1, -1}, pg_threads[2] = {0, 0};  // co-resident grid of the plain / peer-memory variant (-1: not queried)
     unsigned long long *pdone = nullptr;                // [error | edge_count[2] | pad | done[ctas]]
@@ -656,7 +656,6 @@ static int build_graph(lbm_ctx *c, int src) {
 // persistent multi-step launch (persist.cuh)
 // ----------------------------------------------------------------------------------------------
 static const long long PERSIST_MIN_STEPS = 4;
-static const long long PERSIST_AUTO_NODES = 1LL << 21;  // automatic mode: slabs up to 2 Mi nodes (a step of <= ~50 us)
 
 static bool persist_ok(lbm_ctx *c, long long nsteps) {
     if (!c->opt_persistent || nsteps < PERSIST_MIN_STEPS || c->desc.collision == LBM_ITERATIVE_INIT) return false;
@@ -666,18 +665,13 @@ static bool persist_ok(lbm_ctx *c, long long nsteps) {
     if (p2p && (c->peer_up.info.device == c->desc.device || c->peer_dn.info.device == c->desc.device)) return false;
     const long long N = (long long)c->desc.nx * c->nyl;
     if (N >= (1LL << 32)) return false;
-    if (c->opt_persistent == 2) {
-        // Measured (profiles/r02): on ONE GPU graph replays of the per-step launches beat the persistent kernel at every
-        // size (128^2: 4.1 vs 9.5 us per step, 1024^2: 27.5 vs 32.2 us) -- its per-step neighbour hand-shake costs more
-        // than a kernel boundary inside a graph.  Automatic mode therefore only considers it for y-slabs, where it
-        // replaces two launches + fork/join events per step.
-        if (!p2p || N > PERSIST_AUTO_NODES) return false;
-        // Float32 fast contexts on narrow lattices have the packed two-node kernel, which the persistent kernel does not
-        // use: only worth it where launches dominate
-        if (c->desc.dtype == LBM_F32 && c->desc.arith == LBM_ARITH_FAST && c->li.Q <= 13 && c->desc.collision != LBM_MRT &&
-            c->desc.nx % 2 == 0 && N > (1LL << 18))
-            return false;
-    }
+    // Automatic mode (2) never selects it.  Measured in round 2 (profiles/r02): on ONE GPU graph replays of the per-step
+    // launches beat the persistent kernel at every size (128^2: 4.1 vs 9.5 us per step, 1024^2: 27.5 vs 32.2 us), and on
+    // 2 x B200 y-slabs of 1024 x 1024 it ran at 32.1 GLUPS against 59.8 GLUPS for boundary + interior launches from graphs
+    // (r9_C3q_n2_p1 / _p0): every step ends with threadfence -> release -> acquire -> L2-latency reload in every CTA,
+    // which costs more than a kernel boundary inside a graph.  It stays available as option persistent = 1 (tests keep it
+    // bit-identical to the oracle).
+    if (c->opt_persistent == 2) return false;
     int &ctas = c->pg_ctas[p2p ? 1 : 0];
     if (ctas < 0) {
         if (is64(c)) c->ops->persist_grid64(c->desc.collision, p2p, &ctas, &c->pg_threads[p2p ? 1 : 0]);
@@ -1551,6 +1545,35 @@ int lbm_reduce_errors(lbm_ctx *c, double tau_visc, double u_max, const lbm_sep_f
 int lbm_reduce_process(lbm_ctx *c, double u_max, const lbm_sep_field *expected, double *out) {
     return reduce_errors_mode(c, 1, 1.0, u_max, expected, out);
 }
+// sum over the local nodes of E^2 for a separable field E(x, y) = c0 + sum_k a_k X_k(x) Y_k(y) (k < 2; a missing table
+// is the constant 1): O(nx + ny) on the host instead of one more accumulator per node on the device
+static double sep_square_sum(const lbm_sep_field &e, int nx, int ny) {
+    double sx[2] = {0, 0}, sy[2] = {0, 0}, xx[2][2] = {{0, 0}, {0, 0}}, yy[2][2] = {{0, 0}, {0, 0}};
+    auto X = [&](int k, int i) { return e.x[k] ? e.x[k][i] : 1.0; };
+    auto Y = [&](int k, int j) { return e.y[k] ? e.y[k][j] : 1.0; };
+    for (int k = 0; k < 2; ++k) {
+        if (e.a[k] == 0.0) continue;
+        for (int i = 0; i < nx; ++i) sx[k] += X(k, i);
+        for (int j = 0; j < ny; ++j) sy[k] += Y(k, j);
+        for (int l = k; l < 2; ++l) {
+            if (e.a[l] == 0.0) continue;
+            double a = 0, b = 0;
+            for (int i = 0; i < nx; ++i) a += X(k, i) * X(l, i);
+            for (int j = 0; j < ny; ++j) b += Y(k, j) * Y(l, j);
+            xx[k][l] = xx[l][k] = a;
+            yy[k][l] = yy[l][k] = b;
+        }
+    }
+    double s = e.c0 * e.c0 * ((double)nx * (double)ny);
+    for (int k = 0; k < 2; ++k) {
+        if (e.a[k] == 0.0) continue;
+        s += 2 * e.c0 * e.a[k] * sx[k] * sy[k];
+        for (int l = 0; l < 2; ++l)
+            if (e.a[l] != 0.0) s += e.a[k] * e.a[l] * xx[k][l] * yy[k][l];
+    }
+    return s;
+}
+
 static int reduce_errors_mode(lbm_ctx *c, int mode, double tau_visc, double u_max, const lbm_sep_field *expected, double *out) {
     if (!c || !expected || !out) return fail(LBM_ERR_INVALID, "null argument");
     if (!(tau_visc > 0) || !(u_max > 0)) return fail(LBM_ERR_INVALID, "tau_visc %g, u_max %g", tau_visc, u_max);
@@ -1609,8 +1632,12 @@ static int reduce_errors_mode(lbm_ctx *c, int mode, double tau_visc, double u_ma
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(h, ea.out, sizeof(h), cudaMemcpyDeviceToHost, c->stream);
+    double sq[8] = {0};
+    if (mode == 0)  // while the kernels run: the sums that involve the expected fields only
+        for (int f = 1; f < 8; ++f) sq[f] = sep_square_sum(expected[f], nx, nyl);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) return fail(LBM_ERR_CUDA, "lbm_reduce_errors: %s", cudaGetErrorString(e));
+    if (mode == 0) { h[2] = sq[1] + sq[2]; h[4] = sq[3]; h[6] = sq[4]; h[8] = sq[5]; h[10] = sq[7]; h[12] = sq[6]; }
     memcpy(out, h, sizeof(h));
     return p2p_check(c);
 }

@@ -914,7 +914,7 @@ def test_bench_contract_small():
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--nx", "256", "--ny", "256", "--steps", "2",
-                          "--warmup", "3", "--inner", "20", "--cpu-n", "128", "--cpu-steps", "10"],
+                          "--warmup", "3", "--inner", "20", "--cpu-n", "128", "--cpu-steps", "10", "--also-shrink", "16"],
                          capture_output=True, text=True, timeout=600, cwd=root)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.strip()]
@@ -929,6 +929,11 @@ def test_bench_contract_small():
     assert d["e2e"]["h2d_bytes_per_step"] == 256 * 256 * 9 * 8 == d["e2e"]["d2h_bytes_per_step"] and d["e2e"]["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert "workload" in d["config"]
+    # the strong-scaling configurations reported next to the headline (here shrunk 16x): all three measured
+    assert [e["preset"] for e in d["also"]] == ["C5s", "C3", "C4"]
+    for e in d["also"]:
+        assert "skipped" not in e, e
+        assert e["value"] > 0 and e["finite"] and e["scaling"] == "strong" and e["gbs_per_gpu"] > 0
 
 
 def test_timer_and_options():

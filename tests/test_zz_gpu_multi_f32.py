@@ -1,5 +1,5 @@
-"""Float32 contexts on y-slabs (the P2P instances of the scalar and of the packed two-nodes-per-thread kernel).  Kept in a
-file that sorts last: written after the round's GPU budget was spent, so its first run on hardware is the driver's."""
+"""Float32 contexts on y-slabs (the P2P instances of the scalar and of the packed two-nodes-per-thread kernel).  First run on
+hardware: round 2, 2 x B200 (profiles/r02/pytest_multi_run9.log)."""
 import numpy as np
 import pytest
 
@@ -49,5 +49,12 @@ def test_float32_slabs(lattice, model, walls, arith):
         want, _ = O.step(cm, qo, bcs, want)
     a = _slabs(lattice, model, walls, 1, arith)
     b = _slabs(lattice, model, walls, 0, arith)
-    assert np.array_equal(a, b), "halo path changes the Float32 result"
-    assert np.abs(a - want).max() / np.abs(want).max() < 1e-5
+    scale = np.abs(want).max()
+    assert np.abs(a - want).max() / scale < 1e-5 and np.abs(b - want).max() / scale < 1e-5
+    if arith == 0:
+        assert np.array_equal(a, b), "halo path changes the Float32 result"
+    else:
+        # fast arithmetic: the boundary rows come from two instantiations of the fused kernel (with / without the peer
+        # stores) in which the compiler is free to contract multiply-adds differently -- last-bit differences that 40
+        # steps amplify to a few ulp (first measured on 2 x B200 in round 2; exact mode is bit-identical)
+        assert np.abs(a - b).max() / scale < 2e-6
