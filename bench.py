@@ -396,14 +396,39 @@ def measured_peak():
 
 
 def ncu_traffic(a):
+    """DRAM bytes per launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum), MEASURED for this run:
+    after the timed region an `ncu` child process captures one fused launch of the same <lattice, model, dtype, arith, grid>
+    through tools/profile_case.py.  -> (bytes or None, source).  Falls back to the committed capture in
+    profiles/traffic.json when ncu cannot run (no binary / no permission to read the counters)."""
+    import shutil
+    ncu = shutil.which("ncu") or ("/usr/local/cuda/bin/ncu" if os.path.exists("/usr/local/cuda/bin/ncu") else None)
+    if ncu and a.config == "C2" and not os.environ.get("LBM_BENCH_NO_NCU"):
+        cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "--print-units", "base",
+               "-k", "regex:k_step", "-s", "4", "-c", "1", "--csv", sys.executable, os.path.join(ROOT, "tools", "profile_case.py"),
+               "--lattice", a.lattice, "--model", a.collision, "--dtype", a.dtype, "--arith", a.arith, "--n", str(a.nx),
+               "--ny", str(a.ny), "--steps", "4", "--variant", str(a.variant)]
+        try:
+            env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0])
+            for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+                env.pop(k, None)
+            out = subprocess.run(cmd, capture_output=True, text=True, timeout=180, env=env).stdout
+            total, seen = 0.0, 0
+            for line in out.splitlines():
+                cells = [c.strip('"') for c in line.split('","')]
+                if len(cells) > 3 and cells[-3] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    total += float(cells[-1].strip('"').replace(",", ""))
+                    seen += 1
+            if seen == 2 and total > 0:
+                return total, "ncu child process after the timed region (one fused launch, this run)"
+        except Exception:
+            pass
     p = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(p):
+    if os.path.exists(p) and a.config == "C2":
         t = json.load(open(p))
-        if a.config != "C2":
-            return None
-        key = f"{a.lattice}_{a.collision}_{a.dtype}_{a.arith}_{a.nx}x{a.ny}"
-        return t.get(key)
-    return None
+        v = t.get(f"{a.lattice}_{a.collision}_{a.dtype}_{a.arith}_{a.nx}x{a.ny}")
+        if v is not None:
+            return v, "profiles/traffic.json (committed ncu capture; ncu unavailable in this run)"
+    return None, "not measured"
 
 
 def run_b200(a):
@@ -489,7 +514,6 @@ def run_b200(a):
     kern_ms = dev_ms / (a.steps * inner)  # one fused kernel per lattice step (world == 1)
     peak, peak_src = measured_peak()
     achieved = b_alg * nx * nyl / (kern_ms * 1e-3) / 1e9
-    traffic = ncu_traffic(a)
 
     # ---- e2e: host buffers in and out through the C ABI --------------------------------------
     e2e = None
@@ -523,6 +547,7 @@ def run_b200(a):
                "sample": f"{a.cpu_n}x{a.cpu_n} grid, {a.cpu_steps} lattice steps ({secs:.1f} s), C restatement "
                          f"(oracle/lbm_oracle.c) with OpenMP over rows"}
     ctx.close()
+    traffic, traffic_src = ncu_traffic(a) if rank == 0 else (None, None)
     parity = None if a.no_parity else parity_check(world, rank, local, comm, lbm, torch, dist)
     headline = a.config == "C2" and ((a.nx, a.ny) == (4096, 4096) or a.also_shrink > 1)
     also = None if (a.no_also or not headline) else also_cases(a, world, rank, local, comm, lbm, torch, dist, peak)
@@ -543,7 +568,7 @@ def run_b200(a):
             "e2e": e2e,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "bytes_per_update": b_alg,
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "bytes_per_update": b_alg,
                          "kernel_ms": kern_ms, "kernel": "k_step<%s, %s, pull>" % (type(cm).__name__, a.dtype)},
             "cpu_baseline": cpu,
             "parity_check": parity,

@@ -108,6 +108,7 @@ struct ErrorArgs {
     double *out;         // [16] device
     int nblocks;         // capacity of `partials` (the launcher replaces it by the grid size)
     int rows_per_cta;    // set by the launcher
+    const double *tx[16], *ty[16];  // per slot: X table (nx entries), Y table (nyl entries) -- set by the launcher from tab
     unsigned mask;       // bit 2 f + k: term k of field f has a non-zero coefficient (set by the launcher)
     int mode;            // 0: TrackHydrodynamicErrors sums, 1: the sums of process! (CompareWithAnalyticalSolution)
 };

@@ -742,6 +742,17 @@ __device__ __forceinline__ void fields_of(const T (&f)[Q], double &rho, double &
         });
         const double inv = 1.0 / rho;
         ux = jx * inv; uy = jy * inv;
+        // a_bar_2 = sum(f H2(c)) with H2(c) = c c - delta / css (hermite_polynomials.jl:47-51): integer-coefficient sums
+        // (adds for |c| = 1) and one multiply-add by 1 / css, instead of 3 Q multiply-adds by table entries
+        double pxx = 0, pxy = 0, pyy = 0;
+        static_for<0, Q>([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            if constexpr (L::cx(i) * L::cx(i) != 0) pxx = pxx + cmul<L::cx(i) * L::cx(i)>(g[i]);
+            if constexpr (L::cx(i) * L::cy(i) != 0) pxy = pxy + cmul<L::cx(i) * L::cy(i)>(g[i]);
+            if constexpr (L::cy(i) * L::cy(i) != 0) pyy = pyy + cmul<L::cy(i) * L::cy(i)>(g[i]);
+        });
+        axx = pxx - c.cs_inv * rho; axy = pxy; ayy = pyy - c.cs_inv * rho;
+        return;
     }
 #else
     double drho_unused;
@@ -959,12 +970,11 @@ __device__ __forceinline__ void process_terms(double rho, double ux, double uy, 
 //   9 (e_syy-syy)^2  10 e_syy^2  11 (e_syx-syx)^2  12 e_syx^2  13 rho  14 rho (ux+uy)  15 rho (ux^2+uy^2)
 // MODE 0: those sums, MODE 1: the sums of process!.  Terms whose coefficient is zero (most fields of most problems have
 // one term or none) are skipped by a launch-uniform branch, so their tables are never read.
-template <typename T, bool PULL, int MODE>
-__global__ void __launch_bounds__(256, 3) k_errors(const __grid_constant__ KParams<T> p, const __grid_constant__ ErrorArgs ea) {
+template <typename T, bool PULL, int MODE, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_errors(const __grid_constant__ KParams<T> p, const __grid_constant__ ErrorArgs ea) {
     double acc[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) acc[k] = 0;
-    const unsigned W = (unsigned)(p.nx + p.nyl);
     const double half_inv_tau = 1 / (2 * ea.tau_visc);
     const InvConst den(1 + 1 / (2 * ea.tau_visc)), u_max(ea.u_max);
     const double fac = 1 / (ea.u_max * ea.u_max);
@@ -972,21 +982,20 @@ __global__ void __launch_bounds__(256, 3) k_errors(const __grid_constant__ KPara
     const int y0 = blockIdx.y * ea.rows_per_cta, y1 = min(p.nyl, y0 + ea.rows_per_cta);
     const unsigned mask = ea.mask;
     if (x < p.nx) {
-        // slot s = 2 f + k of the tables: X_s at tab[s W + x], Y_s at tab[s W + nx + y]; 32-bit offsets from two bases
-        const double *__restrict__ tx = ea.tab + x;
+        // slot s = 2 f + k of the tables: X_s = ea.tx[s], Y_s = ea.ty[s] (pointers in the parameter block, so that an
+        // address is one multiply-add like the population loads)
 #pragma unroll 1
         for (int y = y0 + threadIdx.y; y < y1; y += blockDim.y) {
             double rho, ux, uy, axx, axy, ayy;
             node_fields<T, PULL>(p, x, y, rho, ux, uy, axx, axy, ayy);
-            const double *__restrict__ ty = ea.tab + (p.nx + y);
             double e[8];
 #pragma unroll
             for (int f = 0; f < 8; ++f) {
                 double v = ea.c0[f];
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
-                    const unsigned s = 2 * f + k;
-                    if (mask & (1u << s)) v = v + ea.a[f][k] * (__ldg(tx + s * W) * __ldg(ty + s * W));
+                    const int s = 2 * f + k;
+                    if (mask & (1u << s)) v = v + ea.a[f][k] * (__ldg(ea.tx[s] + (unsigned)x) * __ldg(ea.ty[s] + (unsigned)y));
                 }
                 e[f] = v;
             }
@@ -1324,16 +1333,26 @@ static void launch_errors(bool pull, const KParams<T> &p, const ErrorArgs &e, cu
     const dim3 grid = reduce_grid(p.nx, p.nyl, block, e.nblocks, &ea.rows_per_cta);
     ea.nblocks = grid.x * grid.y;
     ea.mask = 0;
+    const size_t W = (size_t)p.nx + (size_t)p.nyl;
     for (int f = 0; f < 8; ++f)
-        for (int k = 0; k < 2; ++k)
-            if (ea.a[f][k] != 0.0) ea.mask |= 1u << (2 * f + k);
-    if (ea.mode == 0) {
-        if (pull) k_errors<T, true, 0><<<grid, block, 0, s>>>(p, ea);
-        else k_errors<T, false, 0><<<grid, block, 0, s>>>(p, ea);
-    } else {
-        if (pull) k_errors<T, true, 1><<<grid, block, 0, s>>>(p, ea);
-        else k_errors<T, false, 1><<<grid, block, 0, s>>>(p, ea);
+        for (int k = 0; k < 2; ++k) {
+            const int sl = 2 * f + k;
+            if (ea.a[f][k] != 0.0) ea.mask |= 1u << sl;
+            ea.tx[sl] = ea.tab + (size_t)sl * W;
+            ea.ty[sl] = ea.tab + (size_t)sl * W + p.nx;
+        }
+    // CTAs per SM (measured on B200, 4096^2 D2Q9 f64, profiles/r02/diag_D2Q9_minb*.json): the 10 accumulators + stresses of
+    // TrackHydrodynamicErrors want 80 registers (3 CTAs: 0.49 ms, 4 CTAs with spills: 0.53 ms); the lighter process! sums
+    // run best at 64 registers (4 CTAs: 0.28 ms, 3 CTAs: 0.30 ms).  LBM_ERRORS_MINB=3|4 overrides both (tuning hook).
+    static const int forced = [] { const char *e = getenv("LBM_ERRORS_MINB"); return e ? atoi(e) : 0; }();
+#define LBM_KE(MODE_, MINB_)                                                        \
+    {                                                                               \
+        if (pull) k_errors<T, true, MODE_, MINB_><<<grid, block, 0, s>>>(p, ea);    \
+        else k_errors<T, false, MODE_, MINB_><<<grid, block, 0, s>>>(p, ea);        \
     }
+    if (ea.mode == 0) { if (forced == 4) LBM_KE(0, 4) else LBM_KE(0, 3) }
+    else { if (forced == 3) LBM_KE(1, 3) else LBM_KE(1, 4) }
+#undef LBM_KE
     k_final_sum<<<16, 256, 0, s>>>(ea.partials, ea.nblocks, 16, ea.out);
 }
 

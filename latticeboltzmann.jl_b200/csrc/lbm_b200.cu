@@ -13,6 +13,7 @@
 #include <mutex>
 #include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <type_traits>
@@ -187,6 +188,10 @@ struct lbm_ctx {
     size_t err_doubles = 0;
     std::vector<double> err_tab, scratch_row;  // host copy of the tables on the device, per (field, term) slot
     unsigned err_tab_valid = 0;                // bit slot: err_tab[slot] is what the device holds
+    // page-locked chunk buffers for copies from / to pageable host arrays (HostPipe)
+    char *pipe_pin[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t pipe_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t pipe_bytes = 0;
     // lbm_moments output fields on the device, kept between calls
     double *mom_dev = nullptr;
     size_t mom_bytes = 0;
@@ -817,6 +822,10 @@ void lbm_destroy(lbm_ctx *c) {
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     if (c->snap_dev) cudaFree(c->snap_dev);
     if (c->mom_dev) cudaFree(c->mom_dev);
+    for (int k = 0; k < 4; ++k) {
+        if (c->pipe_pin[k]) cudaFreeHost(c->pipe_pin[k]);
+        if (c->pipe_ev[k]) cudaEventDestroy(c->pipe_ev[k]);
+    }
     if (c->snap_host) cudaFreeHost(c->snap_host);
     for (cudaEvent_t e : {c->ev_snap, c->ev_snap_done})
         if (e) cudaEventDestroy(e);
@@ -968,6 +977,102 @@ static int refresh_ghosts(lbm_ctx *c, int b) {
     return 0;
 }
 
+static bool is_pinned(const void *p);
+
+// memcpy split over a few host threads: one thread moves ~10 GB/s, PCIe 5 x16 takes 55 GB/s
+static void par_memcpy(void *dst, const void *src, size_t bytes) {
+    static const int nthreads = [] {
+        const char *e = getenv("LBM_COPY_THREADS");
+        int n = e ? atoi(e) : (int)std::thread::hardware_concurrency() / 2;
+        return n < 1 ? 1 : (n > 8 ? 8 : n);
+    }();
+    if (bytes < (1u << 20) || nthreads == 1) { memcpy(dst, src, bytes); return; }
+    const size_t slice = ((bytes + nthreads - 1) / nthreads + 63) & ~(size_t)63;
+    std::thread th[8];
+    int started = 0;
+    for (int t = 1; t < nthreads; ++t) {
+        const size_t off = (size_t)t * slice;
+        if (off >= bytes) break;
+        const size_t n = bytes - off < slice ? bytes - off : slice;
+        th[started++] = std::thread([=] { memcpy((char *)dst + off, (const char *)src + off, n); });
+    }
+    memcpy(dst, src, slice < bytes ? slice : bytes);
+    for (int t = 0; t < started; ++t) th[t].join();
+}
+
+// Copies between PAGEABLE host arrays (what a caller's plain Array / numpy array is) and pitched device memory, pipelined
+// through four page-locked chunk buffers: while the DMA engine moves chunk j, host threads copy chunk j + 1 (upload) or
+// chunk j - 1 (download) between the caller's array and the page-locked buffer.  cudaMemcpy from pageable memory does the
+// same staging inside the driver on one thread (6-10 GB/s measured); this path is bound by PCIe instead.  Page-locked
+// arrays (lbm_host_alloc) skip it.
+struct HostPipe {
+    static constexpr int K = 4;
+    static constexpr size_t CHUNK = 8u << 20;
+    lbm_ctx *c;
+    struct Slot { char *host = nullptr; size_t bytes = 0; bool busy = false; } slot[K];
+    int next = 0;
+
+    explicit HostPipe(lbm_ctx *c_) : c(c_) {}
+    int prepare(size_t rowbytes) {
+        const size_t need = rowbytes > CHUNK ? rowbytes : CHUNK;
+        if (c->pipe_bytes >= need) return 0;
+        for (int k = 0; k < K; ++k) {
+            if (c->pipe_pin[k]) { cudaFreeHost(c->pipe_pin[k]); c->pipe_pin[k] = nullptr; }
+            cudaError_t e = cudaHostAlloc((void **)&c->pipe_pin[k], need, cudaHostAllocDefault);
+            if (e != cudaSuccess) { cudaGetLastError(); c->pipe_bytes = 0; return fail(LBM_ERR_NOMEM, "cudaHostAlloc(%zu bytes of copy staging): %s", need, cudaGetErrorString(e)); }
+            if (!c->pipe_ev[k]) CU(cudaEventCreateWithFlags(&c->pipe_ev[k], cudaEventDisableTiming));
+        }
+        c->pipe_bytes = need;
+        return 0;
+    }
+    int retire(int k) {  // wait for slot k's DMA; a download then lands in the caller's array
+        if (!slot[k].busy) return 0;
+        CU(cudaEventSynchronize(c->pipe_ev[k]));
+        if (slot[k].host) par_memcpy(slot[k].host, c->pipe_pin[k], slot[k].bytes);
+        slot[k].busy = false;
+        return 0;
+    }
+    // `rows` rows of `rowbytes` bytes: host contiguous, device with pitch `dpitch`
+    int put(char *dev, size_t dpitch, const char *host, size_t rowbytes, size_t rows) {
+        int rc = prepare(rowbytes);
+        if (rc) return rc;
+        const size_t per = c->pipe_bytes / rowbytes;
+        for (size_t r = 0; r < rows; r += per) {
+            const size_t n = rows - r < per ? rows - r : per;
+            const int k = next;
+            next = (next + 1) % K;
+            if ((rc = retire(k))) return rc;
+            par_memcpy(c->pipe_pin[k], host + r * rowbytes, n * rowbytes);
+            CU(cudaMemcpy2DAsync(dev + r * dpitch, dpitch, c->pipe_pin[k], rowbytes, rowbytes, n, cudaMemcpyHostToDevice, c->stream));
+            CU(cudaEventRecord(c->pipe_ev[k], c->stream));
+            slot[k].host = nullptr; slot[k].bytes = 0; slot[k].busy = true;
+        }
+        return 0;
+    }
+    int get(const char *dev, size_t dpitch, char *host, size_t rowbytes, size_t rows) {
+        int rc = prepare(rowbytes);
+        if (rc) return rc;
+        const size_t per = c->pipe_bytes / rowbytes;
+        for (size_t r = 0; r < rows; r += per) {
+            const size_t n = rows - r < per ? rows - r : per;
+            const int k = next;
+            next = (next + 1) % K;
+            if ((rc = retire(k))) return rc;
+            CU(cudaMemcpy2DAsync(c->pipe_pin[k], rowbytes, dev + r * dpitch, dpitch, rowbytes, n, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaEventRecord(c->pipe_ev[k], c->stream));
+            slot[k].host = host + r * rowbytes; slot[k].bytes = n * rowbytes; slot[k].busy = true;
+        }
+        return 0;
+    }
+    int drain() {
+        for (int i = 0; i < K; ++i) {
+            int rc = retire((next + i) % K);
+            if (rc) return rc;
+        }
+        return 0;
+    }
+};
+
 // host rows [y0, y0+ny) of the local slab ([q][ny][nx]) -> device buffer b
 static int upload_buffer(lbm_ctx *c, int b, const double *f, int y0 = 0, int ny = -1) {
     const int nx = c->desc.nx, Q = c->li.Q;
@@ -975,9 +1080,19 @@ static int upload_buffer(lbm_ctx *c, int b, const double *f, int y0 = 0, int ny 
     if (ny == 0) return 0;
     if (is64(c)) {
         double *o = origin<double>(c, b) + (size_t)y0 * c->pitch;
-        for (int i = 0; i < Q; ++i)
-            CU(cudaMemcpy2DAsync(o + (size_t)i * c->plane, c->pitch * 8, f + (size_t)i * ny * nx, (size_t)nx * 8,
-                                 (size_t)nx * 8, ny, cudaMemcpyHostToDevice, c->stream));
+        if (is_pinned(f)) {
+            for (int i = 0; i < Q; ++i)
+                CU(cudaMemcpy2DAsync(o + (size_t)i * c->plane, c->pitch * 8, f + (size_t)i * ny * nx, (size_t)nx * 8,
+                                     (size_t)nx * 8, ny, cudaMemcpyHostToDevice, c->stream));
+        } else {
+            HostPipe pipe(c);
+            for (int i = 0; i < Q; ++i) {
+                int rc = pipe.put((char *)(o + (size_t)i * c->plane), c->pitch * 8, (const char *)(f + (size_t)i * ny * nx), (size_t)nx * 8, ny);
+                if (rc) return rc;
+            }
+            int rc = pipe.drain();
+            if (rc) return rc;
+        }
     } else {
         int rc = need_stage(c, (size_t)ny * nx * 8);
         if (rc) return rc;
@@ -985,8 +1100,16 @@ static int upload_buffer(lbm_ctx *c, int b, const double *f, int y0 = 0, int ny 
         KParams<float> p = make_params<float>(c, b, b);
         p.dst += (size_t)y0 * c->pitch;
         p.nyl = ny;
+        const bool pinned = is_pinned(f);
+        HostPipe pipe(c);
         for (int i = 0; i < Q; ++i) {
-            CU(cudaMemcpyAsync(stage, f + (size_t)i * ny * nx, (size_t)ny * nx * 8, cudaMemcpyHostToDevice, c->stream));
+            if (pinned) {
+                CU(cudaMemcpyAsync(stage, f + (size_t)i * ny * nx, (size_t)ny * nx * 8, cudaMemcpyHostToDevice, c->stream));
+            } else {
+                int rc2 = pipe.put((char *)stage, (size_t)nx * 8, (const char *)(f + (size_t)i * ny * nx), (size_t)nx * 8, ny);
+                if (!rc2) rc2 = pipe.drain();
+                if (rc2) return rc2;
+            }
             c->ops->import32(p, stage, i, c->stream);
             c->launches += 1;
         }
@@ -1032,9 +1155,19 @@ static int download_buffer(lbm_ctx *c, int b, double *f, int y0 = 0, int ny = -1
     if (ny == 0) return 0;
     if (is64(c)) {
         const double *o = origin<double>(c, b) + (size_t)y0 * c->pitch;
-        for (int i = 0; i < Q; ++i)
-            CU(cudaMemcpy2DAsync(f + (size_t)i * ny * nx, (size_t)nx * 8, o + (size_t)i * c->plane, c->pitch * 8,
-                                 (size_t)nx * 8, ny, cudaMemcpyDeviceToHost, c->stream));
+        if (is_pinned(f)) {
+            for (int i = 0; i < Q; ++i)
+                CU(cudaMemcpy2DAsync(f + (size_t)i * ny * nx, (size_t)nx * 8, o + (size_t)i * c->plane, c->pitch * 8,
+                                     (size_t)nx * 8, ny, cudaMemcpyDeviceToHost, c->stream));
+        } else {
+            HostPipe pipe(c);
+            for (int i = 0; i < Q; ++i) {
+                int rc = pipe.get((const char *)(o + (size_t)i * c->plane), c->pitch * 8, (char *)(f + (size_t)i * ny * nx), (size_t)nx * 8, ny);
+                if (rc) return rc;
+            }
+            int rc = pipe.drain();
+            if (rc) return rc;
+        }
     } else {
         int rc = need_stage(c, (size_t)ny * nx * 8);
         if (rc) return rc;
@@ -1042,10 +1175,19 @@ static int download_buffer(lbm_ctx *c, int b, double *f, int y0 = 0, int ny = -1
         KParams<float> p = make_params<float>(c, b, b);
         p.src += (size_t)y0 * c->pitch;
         p.nyl = ny;
+        const bool pinned = is_pinned(f);
+        HostPipe pipe(c);
         for (int i = 0; i < Q; ++i) {
             c->ops->export32(p, stage, i, c->stream);
             c->launches += 1;
-            CU(cudaMemcpyAsync(f + (size_t)i * ny * nx, stage, (size_t)ny * nx * 8, cudaMemcpyDeviceToHost, c->stream));
+            if (pinned) {
+                CU(cudaMemcpyAsync(f + (size_t)i * ny * nx, stage, (size_t)ny * nx * 8, cudaMemcpyDeviceToHost, c->stream));
+            } else {
+                // (the single staging plane is rewritten by the next export: finish this plane's copy first)
+                int rc2 = pipe.get((const char *)stage, (size_t)nx * 8, (char *)(f + (size_t)i * ny * nx), (size_t)nx * 8, ny);
+                if (!rc2) rc2 = pipe.drain();
+                if (rc2) return rc2;
+            }
         }
     }
     CU(cudaStreamSynchronize(c->stream));

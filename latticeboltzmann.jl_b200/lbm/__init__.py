@@ -7,7 +7,7 @@ benchmarks and notebooks use); Julia's `f!` is spelled `f_`.  Arrays are Float64
 (NX, NY, Q) in Fortran order, i.e. exactly Julia's `f[x, y, i]` memory.
 """
 from . import _abi
-from ._abi import LbmError
+from ._abi import LbmError, pinned_empty
 from .batch import BatchResult, simulate_many
 from .boundary_conditions import (BoundaryCondition, BounceBack, Direction, East, MovingWall, North, South, West)
 from .collision_models import (MRT, SRT, TRT, CollisionModel, IterativeInitializationCollisionModel, LatticeForce,
@@ -16,8 +16,8 @@ from .initial_conditions import (AnalyticalEquilibrium, AnalyticalEquilibriumAnd
                                  AnalyticalVelocityAndStress, ConstantDensity, InitializationStrategy,
                                  IterativeInitialization, IterativeInitializationMeiEtAl,
                                  ZeroVelocityInitialCondition, initialize, initialize_mei_et_al, initialize_on_device)
-from .model import (DeviceState, LatticeBoltzmannModel, apply_, apply_boundary_conditions_, collide_,
-                    collide_model_, next_model_, simulate, simulate_model, stream, stream_, stream_model_)
+from .model import (DeviceState, LatticeBoltzmannModel, apply_, apply_boundary_conditions_, clear_scratch_contexts,
+                    collide_, collide_model_, next_model_, simulate, simulate_model, stream, stream_, stream_model_)
 from .parallel import SlabComm, halo_rows_per_direction, slab_rows
 from .problems import (CouetteFlow, DecayingShearFlow, FluidFlowProblem, LidDrivenCavityFlow,
                        LinearizedThermalDiffusion, LinearizedTransverseShearWave, PoiseuilleFlow, TGV,

@@ -314,6 +314,15 @@ def _scratch(q, cm, bcs, f, dtype="f64", arith="exact"):
     return ctx, f
 
 
+def _direct_out(ctx, f_out):
+    """f_out if the library can write the result straight into it (Fortran-ordered float64 of the context's shape), else
+    None: the result is then downloaded into a new array and assigned -- one more pass over host memory"""
+    if (isinstance(f_out, np.ndarray) and f_out.dtype == np.float64 and f_out.shape == ctx.shape and f_out.flags.f_contiguous
+            and f_out.flags.writeable):
+        return f_out
+    return None
+
+
 def _release(ctx):
     """end of an array-level call: cached scratch contexts stay alive, the others are destroyed"""
     if not any(c is ctx for c in _SCRATCH_CACHE.values()):
@@ -341,10 +350,11 @@ def collide_(collision_model, q, f_in=None, f_out=None, *, time=0.0, f_old=None,
         ctx.upload_f(f)
         st.prepare_force_time(time)
         ctx.collide(0, time)
-        out = ctx.download_f_collision()
+        direct = _direct_out(ctx, f_out)
+        out = ctx.download_f_collision(direct)
     finally:
         _release(ctx)
-    if f_out is not None:
+    if f_out is not None and direct is None:
         f_out[...] = out
     return out
 
@@ -356,10 +366,11 @@ def stream_(q, f=None, f_new=None, *, f_old=None, dtype="f64"):
     try:
         ctx.upload_f_collision(f)
         ctx.stream()
-        out = ctx.download_f()
+        direct = _direct_out(ctx, f_new)
+        out = ctx.download_f(direct)
     finally:
         _release(ctx)
-    if f_new is not None:
+    if f_new is not None and direct is None:
         f_new[...] = out
     return out
 
@@ -389,8 +400,10 @@ def apply_(bcs, q, f_new, f_old, *, time=0.0, dtype="f64"):
         ctx.upload_f(np.asfortranarray(f_new, dtype=np.float64))
         ctx.upload_f_collision(fo)
         ctx.apply_bcs(time)
-        out = ctx.download_f()
+        direct = _direct_out(ctx, f_new)
+        out = ctx.download_f(direct)
     finally:
         _release(ctx)
-    f_new[...] = out
+    if direct is None:
+        f_new[...] = out
     return f_new
