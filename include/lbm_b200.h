@@ -233,6 +233,13 @@ int lbm_init_analytic(lbm_ctx *ctx, const lbm_init_spec *spec);
 /* Page-locked host memory for population arrays that cross the boundary often (snapshots, array-level operators): copies
  * from / to such arrays run at the full PCIe rate and asynchronously.  Plain malloc'ed arrays are accepted everywhere. */
 int lbm_host_alloc(void **ptr, size_t bytes);
+/* lbm_upload_f / lbm_download_f for page-locked arrays WITHOUT the final synchronisation: the copies are enqueued on the
+ * context's stream.  With two contexts in flight, job k + 1's upload and job k - 1's download overlap job k's lbm_step
+ * (PCIe is full duplex), so a stream of independent jobs runs at the device rate instead of copy + compute + copy.
+ * `f` must stay valid (and, for uploads, unmodified) until lbm_sync or another synchronising call on the context.
+ * LBM_ERR_INVALID for pageable arrays. */
+int lbm_upload_f_async(lbm_ctx *ctx, const double *f);
+int lbm_download_f_async(lbm_ctx *ctx, double *f);
 int lbm_host_free(void *ptr);
 
 /* TakeSnapshots.next! (src/processing_methods/take_snapshots.jl:12-29: push!(snapshots, copy(f_in))) without stalling the

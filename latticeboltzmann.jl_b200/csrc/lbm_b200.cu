@@ -1074,7 +1074,7 @@ struct HostPipe {
 };
 
 // host rows [y0, y0+ny) of the local slab ([q][ny][nx]) -> device buffer b
-static int upload_buffer(lbm_ctx *c, int b, const double *f, int y0 = 0, int ny = -1) {
+static int upload_buffer(lbm_ctx *c, int b, const double *f, int y0 = 0, int ny = -1, bool sync = true) {
     const int nx = c->desc.nx, Q = c->li.Q;
     if (ny < 0) ny = c->nyl;
     if (ny == 0) return 0;
@@ -1114,7 +1114,7 @@ static int upload_buffer(lbm_ctx *c, int b, const double *f, int y0 = 0, int ny 
             c->launches += 1;
         }
     }
-    CU(cudaStreamSynchronize(c->stream));
+    if (sync) CU(cudaStreamSynchronize(c->stream));
     return 0;
 }
 
@@ -1149,7 +1149,7 @@ int lbm_upload_f_collision(lbm_ctx *c, const double *f) {
     return 0;
 }
 
-static int download_buffer(lbm_ctx *c, int b, double *f, int y0 = 0, int ny = -1) {
+static int download_buffer(lbm_ctx *c, int b, double *f, int y0 = 0, int ny = -1, bool sync = true) {
     const int nx = c->desc.nx, Q = c->li.Q;
     if (ny < 0) ny = c->nyl;
     if (ny == 0) return 0;
@@ -1190,7 +1190,7 @@ static int download_buffer(lbm_ctx *c, int b, double *f, int y0 = 0, int ny = -1
             }
         }
     }
-    CU(cudaStreamSynchronize(c->stream));
+    if (sync) CU(cudaStreamSynchronize(c->stream));
     return 0;
 }
 
@@ -1201,6 +1201,32 @@ int lbm_download_f(lbm_ctx *c, double *f) {
     if (rc) return rc;
     rc = download_buffer(c, c->cur, f);
     return rc ? rc : p2p_check(c);
+}
+
+// Asynchronous forms for page-locked arrays: the copies are enqueued on the context's stream and the call returns; with two
+// contexts in flight job k + 1's upload and job k - 1's download overlap job k's steps (PCIe is full duplex).  lbm_sync
+// (or any synchronising call) completes them; `f` must stay valid and unmodified until then.
+int lbm_upload_f_async(lbm_ctx *c, const double *f) {
+    if (!c || !f) return fail(LBM_ERR_INVALID, "null argument");
+    if (!is_pinned(f)) return fail(LBM_ERR_INVALID, "lbm_upload_f_async needs a page-locked array (lbm_host_alloc)");
+    CU(cudaSetDevice(c->desc.device));
+    int rc = wait_comm(c);
+    if (rc) return rc;
+    rc = upload_buffer(c, c->cur, f, 0, -1, false);
+    if (rc) return rc;
+    c->state = ST_STREAM;
+    c->have_coll = false;
+    c->resume_ok = false;
+    return 0;
+}
+
+int lbm_download_f_async(lbm_ctx *c, double *f) {
+    if (!c || !f) return fail(LBM_ERR_INVALID, "null argument");
+    if (!is_pinned(f)) return fail(LBM_ERR_INVALID, "lbm_download_f_async needs a page-locked array (lbm_host_alloc)");
+    CU(cudaSetDevice(c->desc.device));
+    int rc = materialize(c);
+    if (rc) return rc;
+    return download_buffer(c, c->cur, f, 0, -1, false);
 }
 
 int lbm_host_alloc(void **ptr, size_t bytes) {

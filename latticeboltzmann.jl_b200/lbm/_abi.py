@@ -38,7 +38,7 @@ EXPORTS = [
     "lbm_collide", "lbm_stream", "lbm_apply_bcs", "lbm_step", "lbm_sync", "lbm_moments", "lbm_reduce",
     "lbm_reduce_errors", "lbm_reduce_process",
     "lbm_kernel_launches", "lbm_halo_path", "lbm_last_step_ms", "lbm_timer_start", "lbm_timer_stop", "lbm_set_option",
-    "lbm_init_analytic", "lbm_host_alloc", "lbm_host_free", "lbm_snapshot_begin", "lbm_snapshot_end",
+    "lbm_init_analytic", "lbm_host_alloc", "lbm_host_free", "lbm_upload_f_async", "lbm_download_f_async", "lbm_snapshot_begin", "lbm_snapshot_end",
     "lbm_batch_create", "lbm_batch_destroy", "lbm_batch_set_tau", "lbm_batch_set_force_uniform", "lbm_batch_upload_f",
     "lbm_batch_broadcast_f", "lbm_batch_download_f", "lbm_batch_run", "lbm_batch_status", "lbm_batch_reduce_errors",
     "lbm_batch_last_run_ms", "lbm_batch_kernel_launches",
@@ -137,6 +137,8 @@ def lib():
     l.lbm_init_analytic.argtypes = [vp, C.POINTER(lbm_init_spec)]
     l.lbm_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
     l.lbm_host_free.argtypes = [vp]
+    l.lbm_upload_f_async.argtypes = [vp, vp]
+    l.lbm_download_f_async.argtypes = [vp, vp]
     l.lbm_snapshot_begin.argtypes = [vp, vp]
     l.lbm_snapshot_end.argtypes = [vp]
     l.lbm_batch_create.argtypes = [C.POINTER(lbm_desc), C.c_int32, C.POINTER(vp)]
@@ -272,6 +274,15 @@ class Context:
     def download_f(self, out=None):
         out = self.new_f() if out is None else self._check_f(out, True)
         check(lib().lbm_download_f(self._h, out.ctypes.data))
+        return out
+
+    def upload_f_async(self, f):
+        """upload_f for a page-locked array (pinned_empty) without waiting: returns once the copies are enqueued"""
+        check(lib().lbm_upload_f_async(self._h, self._check_f(f).ctypes.data))
+
+    def download_f_async(self, out):
+        """download_f into a page-locked array without waiting; valid after sync()"""
+        check(lib().lbm_download_f_async(self._h, self._check_f(out, True).ctypes.data))
         return out
 
     def snapshot_begin(self, out=None):

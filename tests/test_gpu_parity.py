@@ -936,6 +936,42 @@ def test_bench_contract_small():
         assert e["value"] > 0 and e["finite"] and e["scaling"] == "strong" and e["gbs_per_gpu"] > 0
 
 
+def test_asynchronous_copies_with_two_contexts_in_flight(oracle):
+    """lbm_upload_f_async / lbm_download_f_async (page-locked arrays): a stream of independent jobs alternating between two
+    contexts -- the bench's e2e pipeline -- returns for every job exactly what the synchronous calls return, and the
+    oracle's result; pageable arrays are refused."""
+    O = oracle
+    qo = O.L.D2Q9()
+    nx, ny, nsteps = 96, 50, 23
+    cm = O.TRT(0.8, 1.1, (1e-6, 0.0))
+    jobs = [random_populations(qo, nx, ny, seed=10 + k) for k in range(5)]
+    want = [None] * len(jobs)
+    for k, f in enumerate(jobs):
+        g = f
+        for _ in range(nsteps):
+            g, _ = O.step(cm, qo, [], g)
+        want[k] = g
+    ins = [lbm.pinned_empty((nx, ny, 9)) for _ in jobs]
+    outs = [lbm.pinned_empty((nx, ny, 9)) for _ in jobs]
+    for a, f in zip(ins, jobs):
+        a[...] = to_host_layout(f)
+    with _abi.Context(nx, ny, "D2Q9", _abi.TRT, [0.8, 1.1]) as c0, _abi.Context(nx, ny, "D2Q9", _abi.TRT, [0.8, 1.1]) as c1:
+        for c in (c0, c1):
+            c.set_force_uniform(1e-6, 0.0)
+        for k in range(len(jobs)):
+            c = (c0, c1)[k % 2]
+            c.upload_f_async(ins[k])
+            c.step(0, nsteps)
+            c.download_f_async(outs[k])
+        c0.sync(); c1.sync()
+        for k in range(len(jobs)):
+            assert np.array_equal(to_oracle_layout(outs[k]), want[k]), k
+        with pytest.raises(lbm.LbmError):
+            c0.upload_f_async(np.asfortranarray(ins[0].copy()))
+        with pytest.raises(lbm.LbmError):
+            c0.download_f_async(c0.new_f())
+
+
 def test_timer_and_options():
     with _abi.Context(64, 64, "D2Q9", _abi.SRT, [0.9]) as c:
         c.upload_f(np.asfortranarray(np.ones((64, 64, 9)) * lbm.D2Q9().weights))
