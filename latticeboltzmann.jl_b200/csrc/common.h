@@ -222,6 +222,9 @@ struct Ops {
     // f_stream of the current state as compact Float64 [Q][nyl][nx] (pull: the state holds post-collision populations)
     void (*snapshot64)(bool pull, const KParams<double> &p, double *out, cudaStream_t s);
     void (*snapshot32)(bool pull, const KParams<float> &p, double *out, cudaStream_t s);
+    // TMA-staged fused pull step (tma.cuh); tmap: CUtensorMap of the source buffer; returns -1 when not available
+    int (*step_tma64)(int cm, const KParams<double> &p, const void *tmap, long long step, int gx, int gy, int cfg, cudaStream_t s);
+    int (*step_tma32)(int cm, const KParams<float> &p, const void *tmap, long long step, int gx, int gy, int cfg, cudaStream_t s);
     // persistent multi-step kernel: co-resident grid (CTAs, threads) for this <collision model, dtype>, 0 CTAs if the
     // device cannot launch cooperatively; pa: src = current state, pb: the two buffers swapped
     void (*persist_grid64)(int cm, bool p2p, int *ctas, int *threads);

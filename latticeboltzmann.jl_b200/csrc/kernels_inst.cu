@@ -1154,6 +1154,7 @@ static inline dim3 grid_for(const KParams<T> &p, const dim3 &block, int rows, in
 }
 
 #include "packed_f32.cuh"
+#include "tma.cuh"
 
 // Launch configuration of the fused kernel per <collision model, dtype>: {MINB, NPT, CTA threads},
 // chosen from tools/sweep.py runs on B200 (profiles/r01_sweep_summary.md).
@@ -1395,6 +1396,7 @@ static const Ops ops = {
     &launch_init_eq<double>, &launch_init_eq<float>,
     &launch_init_analytic<double>, &launch_init_analytic<float>,
     &launch_snapshot<double>, &launch_snapshot<float>,
+    &launch_step_tma<double>, &launch_step_tma<float>,
     &persist_grid<double>, &persist_grid<float>,
     &launch_persist<double>, &launch_persist<float>,
     &launch_batch<double>, &launch_batch<float>,

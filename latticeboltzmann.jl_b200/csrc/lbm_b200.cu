@@ -13,6 +13,7 @@
 #include <mutex>
 #include <algorithm>
 #include <string>
+#include <cuda.h>
 #include <thread>
 #include <vector>
 
@@ -188,6 +189,11 @@ struct lbm_ctx {
     size_t err_doubles = 0;
     std::vector<double> err_tab, scratch_row;  // host copy of the tables on the device, per (field, term) slot
     unsigned err_tab_valid = 0;                // bit slot: err_tab[slot] is what the device holds
+    // TMA-staged fused step (tma.cuh): the two population buffers as 3-D tensor maps (pitch, rows incl. ghosts, Q)
+    alignas(64) CUtensorMap tmap[2];
+    bool tma_ok = false;
+    int opt_tma = 2;      // 0 = never, 1 = wherever available, 2 = automatic (tma_auto)
+    int opt_tma_cfg = 0;  // tuning: 100 * (CTA width / 128) + 10 * stages + CTAs per SM; 0 = default
     // page-locked chunk buffers for copies from / to pageable host arrays (HostPipe)
     char *pipe_pin[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t pipe_ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -503,12 +509,26 @@ static void fill_p2p(const lbm_ctx *c, KParams<T> &p, int dst) {
 // ----------------------------------------------------------------------------------------------
 // kernel sequencing
 // ----------------------------------------------------------------------------------------------
+// Use the TMA-staged kernel (tma.cuh) for this context's fused pull launches?  Only on request: measured slower than or
+// equal to the register kernel on every <lattice, dtype> (tma.cuh header, profiles/r02/tma_sweep_v2.jsonl), so automatic
+// mode (2) keeps it off.
+static bool tma_wanted(const lbm_ctx *c) {
+    return c->opt_tma == 1 && c->desc.collision != LBM_ITERATIVE_INIT;
+}
+
 template <typename T>
 static void run_step(lbm_ctx *c, bool pull, const KParams<T> &p, long long step, cudaStream_t s = nullptr) {
     if (!s) s = c->stream;
+    c->launches += 1;
+    if (pull && c->tma_ok && tma_wanted(c)) {
+        const int b = (const void *)p.src == (const void *)origin<T>(c, 0) ? 0 : 1;
+        int rc;
+        if (std::is_same<T, double>::value) rc = c->ops->step_tma64(c->desc.collision, reinterpret_cast<const KParams<double> &>(p), &c->tmap[b], step, c->gx, c->gy, c->opt_tma_cfg, s);
+        else rc = c->ops->step_tma32(c->desc.collision, reinterpret_cast<const KParams<float> &>(p), &c->tmap[b], step, c->gx, c->gy, c->opt_tma_cfg, s);
+        if (rc == 0) return;
+    }
     if (std::is_same<T, double>::value) c->ops->step64(c->desc.collision, pull, reinterpret_cast<const KParams<double> &>(p), step, c->opt_variant, s);
     else c->ops->step32(c->desc.collision, pull, reinterpret_cast<const KParams<float> &>(p), step, c->opt_variant, s);
-    c->launches += 1;
 }
 
 // fused launch that also pushes its boundary rows into the neighbours' ghost rows
@@ -661,6 +681,38 @@ static int build_graph(lbm_ctx *c, int src) {
 // persistent multi-step launch (persist.cuh)
 // ----------------------------------------------------------------------------------------------
 static const long long PERSIST_MIN_STEPS = 4;
+
+// The population buffers as tensor maps for cp.async.bulk.tensor (driver entry point resolved at run time: the library
+// does not link libcuda).  Failure just leaves the TMA path off.
+static void make_tensor_maps(lbm_ctx *c) {
+    typedef CUresult (*encode_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_t encode = [] {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) { cudaGetLastError(); fn = nullptr; }
+        return (encode_t)fn;
+    }();
+    c->tma_ok = false;
+    if (!encode) return;
+    const cuuint64_t rows = (cuuint64_t)(c->plane / c->pitch);
+    if ((long long)rows * c->pitch != c->plane) return;  // padded planes (layout experiments): not a regular tensor
+    const cuuint64_t dims[3] = {(cuuint64_t)c->pitch, rows, (cuuint64_t)c->li.Q};
+    const cuuint64_t strides[2] = {(cuuint64_t)c->pitch * c->elt, (cuuint64_t)c->plane * c->elt};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    // box = one row segment of one population: the 128 nodes of a tile plus 4 elements on either side (tma.cuh: the box
+    // must start 16-byte aligned, the x shift of the pull happens in the shared-memory read)
+    const cuuint32_t box[3] = {128 + 8, 1, 1};
+    if (c->gx < 4 || (c->gx * c->elt) % 16 != 0) return;  // narrow grids (4 ghost columns) have no aligned box start
+    for (int b = 0; b < 2; ++b) {
+        CUresult r = encode(&c->tmap[b], c->elt == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, c->buf[b],
+                            dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return;
+    }
+    c->tma_ok = true;
+}
 
 static bool persist_ok(lbm_ctx *c, long long nsteps) {
     if (!c->opt_persistent || nsteps < PERSIST_MIN_STEPS || c->desc.collision == LBM_ITERATIVE_INIT) return false;
@@ -934,6 +986,7 @@ int lbm_create(const lbm_desc *d, lbm_ctx **out) {
             cudaMemset(c->buf[b], 0, bytes);
         }
     }
+    make_tensor_maps(c);
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithPriority(&c->bstream, cudaStreamNonBlocking, -1) != cudaSuccess ||
@@ -1668,6 +1721,8 @@ int lbm_set_option(lbm_ctx *c, const char *key, int64_t value) {
     else if (!strcmp(key, "overlap")) c->opt_overlap = (int)value;
     else if (!strcmp(key, "p2p")) c->opt_p2p = (int)value;
     else if (!strcmp(key, "persistent")) c->opt_persistent = (int)value;
+    else if (!strcmp(key, "tma")) c->opt_tma = (int)value;
+    else if (!strcmp(key, "tma_cfg")) c->opt_tma_cfg = (int)value;
     else return fail(LBM_ERR_INVALID, "unknown option '%s'", key);
     return 0;
 }

@@ -972,6 +972,39 @@ def test_asynchronous_copies_with_two_contexts_in_flight(oracle):
             c0.download_f_async(c0.new_f())
 
 
+@pytest.mark.parametrize("name,model,bck,dtype,arith", [
+    ("D2Q9", "TRT", "poiseuille", _abi.F64, _abi.ARITH_EXACT), ("D2Q37", "TRT", "couette", _abi.F64, _abi.ARITH_EXACT),
+    ("D2Q17", "MRT", "none", _abi.F64, _abi.ARITH_FAST), ("D2Q21", "SRT", "cavity", _abi.F32, _abi.ARITH_EXACT),
+    ("D2Q13", "TRT", "partial", _abi.F64, _abi.ARITH_EXACT),
+])
+def test_tma_staged_kernel_equals_the_register_kernel(oracle, name, model, bck, dtype, arith):
+    """Option tma = 1: the fused pull step with its loads staged through shared memory by cp.async.bulk.tensor (tma.cuh;
+    opt-in, measured slower).  Same device functions after the load, so the result is bit-identical to the register kernel
+    and -- in Float64 exact SRT / TRT -- to the oracle; grids whose rows end inside a box (nx not a multiple of 128, nx <
+    128) exercise the zero-filled part of the boxes."""
+    O = oracle
+    qo = O.L.BY_NAME[name]()
+    for nx, ny, nsteps in ((300, 21, 19), (40, 37, 9)):
+        f0 = random_populations(qo, nx, ny, seed=5)
+        force = (2e-6, 1e-6)
+        cm, code, taus = _models(O, qo, force)[model]
+        ob, hb = _bcs_pair(O, bck, nx, ny)
+        outs = []
+        for tma in (1, 0):
+            with _ctx(name, code, taus, hb, nx, ny, arith, dtype) as c:
+                c.set_option("tma", tma)
+                c.set_force_uniform(*force)
+                c.upload_f(to_host_layout(f0))
+                c.step(0, nsteps)
+                outs.append(to_oracle_layout(c.download_f()))
+        assert np.array_equal(outs[0], outs[1])
+        if dtype == _abi.F64 and arith == _abi.ARITH_EXACT and model != "MRT":
+            want = f0
+            for _ in range(nsteps):
+                want, _ = O.step(cm, qo, ob, want)
+            assert np.array_equal(outs[0], want)
+
+
 def test_timer_and_options():
     with _abi.Context(64, 64, "D2Q9", _abi.SRT, [0.9]) as c:
         c.upload_f(np.asfortranarray(np.ones((64, 64, 9)) * lbm.D2Q9().weights))

@@ -31,6 +31,9 @@ def main():
     ap.add_argument("--ny", type=int, default=0)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--tma", type=int, default=2, help="TMA-staged fused kernel: 0 off, 1 on, 2 automatic")
+    ap.add_argument("--tma-cfg", type=int, default=0, help="100 * (CTA width / 128) + 10 * stages + CTAs per SM; 0 = default")
+    ap.add_argument("--check", action="store_true", help="compare the populations after the run with a run of the register kernel")
     ap.add_argument("--walls", action="store_true")
     ap.add_argument("--persistent", type=int, default=2, help="0: launch per step / graphs, 1: persistent kernel, 2: automatic")
     ap.add_argument("--graph", type=int, default=1)
@@ -59,12 +62,14 @@ def main():
     with _abi.Context(n, ny, a.lattice, code, taus, bcs, dtype=_abi.F64 if a.dtype == "f64" else _abi.F32,
                       arith=_abi.ARITH_FAST if a.arith == "fast" else _abi.ARITH_EXACT) as c:
         c.set_option("variant", a.variant)
+        c.set_option("tma", a.tma)
+        c.set_option("tma_cfg", a.tma_cfg)
         c.set_option("persistent", a.persistent)
         c.set_option("graph", a.graph)
         c.upload_f(f0)
         c.step(0, 4)
         c.sync()
-        out = dict(lattice=a.lattice, model=a.model, dtype=a.dtype, arith=a.arith, variant=a.variant, n=n, ny=ny,
+        out = dict(lattice=a.lattice, model=a.model, dtype=a.dtype, arith=a.arith, variant=a.variant, tma=a.tma, tma_cfg=a.tma_cfg, n=n, ny=ny,
                    persistent=a.persistent, graph=a.graph)
         if a.diag:
             import time
@@ -107,6 +112,15 @@ def main():
             mlups = n * ny / (ms * 1e-3) / 1e6
             gbs = mlups * 1e6 * 2 * q.Q * es / 1e9
             out.update(ms_per_step=round(ms, 5), steps=tot_steps, mlups=round(mlups, 1), gbs=round(gbs, 1), frac=round(gbs / peak, 4))
+            if a.check:
+                res = []
+                for tma in (a.tma, 0):
+                    c.set_option("tma", tma)
+                    c.upload_f(f0)
+                    c.step(0, 7)
+                    res.append(c.download_f())
+                out["check_max_abs_diff_vs_register_kernel"] = float(np.abs(res[0] - res[1]).max())
+                out["check_identical"] = bool(np.array_equal(res[0], res[1]))
         print(json.dumps(out), flush=True)
 
 
