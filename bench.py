@@ -62,6 +62,7 @@ def parse():
     ap.add_argument("--p2p", type=int, default=1, help="N > 1: 1 = peer-memory halo stores (default), 0 = NCCL send/recv")
     ap.add_argument("--graph", type=int, default=1, help="1 = replay CUDA graphs of 16 fused steps (default), 0 = plain launches")
     ap.add_argument("--persistent", type=int, default=2, help="0 = launches per step (graphs), 1 = persistent multi-step kernel wherever possible, 2 = automatic")
+    ap.add_argument("--overlap", type=int, default=-1, help="N > 1, peer memory: 1 = boundary-row launch + interior launch per step, 2 = one merged launch, 0 = whole slab in one launch after the exchange; -1 = the library's default")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-serial", action="store_true", help="e2e with one job at a time only (no further contexts in flight)")
     ap.add_argument("--e2e-jobs", type=int, default=3, help="independent jobs in flight for the e2e figure (N = 1)")
@@ -337,6 +338,8 @@ def also_cases(a, world, rank, local, comm, lbm, torch, dist, peak):
             ctx.set_option("p2p", a.p2p)
             ctx.set_option("graph", a.graph)
             ctx.set_option("persistent", a.persistent)
+            if a.overlap >= 0:
+                ctx.set_option("overlap", a.overlap)
             state = lbm.DeviceState(ctx, q, cm, comm)
             state.prepare_force(0, 1, problem.delta_t())
             t0 = time.perf_counter()
@@ -457,6 +460,8 @@ def run_b200(a):
     ctx.set_option("p2p", a.p2p)
     ctx.set_option("graph", a.graph)
     ctx.set_option("persistent", a.persistent)
+    if a.overlap >= 0:
+        ctx.set_option("overlap", a.overlap)
     halo_path = {0: "none (single GPU)", 1: "NCCL send/recv on a side stream", 2: "peer-memory stores from the boundary-row launch"}[ctx.halo_path]
     nyl = ctx.ny_local
     state = lbm.DeviceState(ctx, q, cm, comm)
@@ -611,7 +616,7 @@ def run_b200(a):
             "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": a.dtype, "data": "synthetic",
             "config": cfg,
-            "details": {"grid_local": [nx, nyl], "variant": a.variant, "cuda_graphs": bool(a.graph), "persistent": a.persistent, "halo_exchange": halo_path,
+            "details": {"grid_local": [nx, nyl], "variant": a.variant, "cuda_graphs": bool(a.graph), "persistent": a.persistent, "overlap": a.overlap, "halo_exchange": halo_path,
                         "wall_ms_per_step": region_ms / a.steps},
             "clocks": clocks,
             "e2e": e2e,

@@ -47,7 +47,11 @@ struct KParams {
     long long pitch, plane;
     int nx, nyl;   // local interior size
     int y0g, nyg;  // first global row of this slab, global row count
-    int row_a0, row_an, row_b0, nrows;  // launched rows r -> local row (r < row_an ? row_a0 + r : row_b0 + r - row_an)
+    // launched rows r -> local row: r < row_an ? row_a0 + r : (r - row_an < row_bn ? row_b0 + r - row_an : row_c0 + r - row_an - row_bn)
+    int row_a0, row_an, row_b0, row_bn, row_c0, nrows;
+    int p2p_rows;  // P2P launches: the first p2p_rows launched rows are the slab's edge rows -- only the CTAs that start
+                   // inside them wait for the neighbours' epoch and publish this one (nrows: every CTA, as in a launch of
+                   // edge rows only)
     int wrap_y;    // 1: this slab is the whole periodic domain in y -> kernels write the y images too
     // collision constants (already converted to T):
     //   SRT: c[0] = 1 - 1/tau, c[1] = 1/tau, shift = tau

@@ -235,7 +235,9 @@ __device__ __forceinline__ void store_node(const KParams<T> &p, int x, int y, T 
 
 template <typename T>
 __device__ __forceinline__ int launched_row(const KParams<T> &p, int r) {
-    return r < p.row_an ? p.row_a0 + r : p.row_b0 + (r - p.row_an);
+    if (r < p.row_an) return p.row_a0 + r;
+    r -= p.row_an;
+    return r < p.row_bn ? p.row_b0 + r : p.row_c0 + (r - p.row_bn);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -590,11 +592,10 @@ __device__ __noinline__ void p2p_store(const KParams<T> &p, int x, int y) {
 // End of a producing launch: every thread makes its (peer) stores visible system-wide, the last CTA to
 // finish publishes the epoch to both neighbours.
 template <typename T>
-__device__ __forceinline__ void p2p_signal(const KParams<T> &p) {
+__device__ __forceinline__ void p2p_signal(const KParams<T> &p, unsigned long long total) {
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0 && threadIdx.y == 0) {
-        const unsigned long long total = (unsigned long long)gridDim.x * gridDim.y;
         if (atomicAdd(p.flags + P2P_CTA_COUNT, 1ULL) == total - 1) {
             p.flags[P2P_CTA_COUNT] = 0;
             __threadfence_system();
@@ -634,8 +635,13 @@ __global__ void k_p2p_set_base(unsigned long long *flags, unsigned long long bas
 template <int CM, typename T, bool PULL, int MINB = 1, int NPT = 1, bool P2P = false>
 __global__ void __launch_bounds__(256, MINB) k_step(const __grid_constant__ KParams<T> p, long long step) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    if constexpr (P2P) p2p_wait(p);
-    else if (x >= p.nx) return;
+    // P2P: CTAs that start inside the slab's edge rows (the first p2p_rows launched rows) take part in the halo protocol;
+    // the others (interior rows of a merged launch) neither wait nor publish
+    bool edge_cta = false;
+    if constexpr (P2P) {
+        edge_cta = (int)(blockIdx.y * blockDim.y) * NPT < p.p2p_rows;
+        if (edge_cta) p2p_wait(p);
+    } else if (x >= p.nx) return;
     for (int r0 = (!P2P || x < p.nx) ? (blockIdx.y * blockDim.y + threadIdx.y) * NPT : p.nrows; r0 < p.nrows; r0 += gridDim.y * blockDim.y * NPT) {
         T f[NPT][Q];
 #pragma unroll
@@ -656,7 +662,14 @@ __global__ void __launch_bounds__(256, MINB) k_step(const __grid_constant__ KPar
                 }
             }
     }
-    if constexpr (P2P) p2p_signal(p);
+    if constexpr (P2P) {
+        if (edge_cta) {
+            const int rows_per_cta = (int)blockDim.y * NPT;
+            int edge_y = (p.p2p_rows + rows_per_cta - 1) / rows_per_cta;
+            if (edge_y > (int)gridDim.y) edge_y = (int)gridDim.y;
+            p2p_signal(p, (unsigned long long)gridDim.x * (unsigned long long)edge_y);
+        }
+    }
 }
 
 // K3: stream (+BC) only:  dst interior = pull(src)

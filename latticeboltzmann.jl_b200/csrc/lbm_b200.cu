@@ -176,7 +176,7 @@ struct lbm_ctx {
     long long launches = 0;
     bool timed = false;
     int opt_variant = 0;
-    int opt_overlap = 1;
+    int opt_overlap = 3;  // y-slabs: 0 whole slab after the exchange, 1 boundary + interior launches, 2 merged launch, 3 automatic
     // persistent multi-step kernel (persist.cuh): 0 = off, 1 = whenever possible, 2 = automatic (= off: measured slower, see persist_ok)
     int opt_persistent = 2;
     int pg_ctas[2] = {-1, -1}, pg_threads[2] = {0, 0};  // co-resident grid of the plain / peer-memory variant (-1: not queried)
@@ -275,7 +275,8 @@ static KParams<T> make_params(const lbm_ctx *c, int src, int dst) {
     p.nyl = c->nyl;
     p.y0g = c->y0;
     p.nyg = c->desc.ny;
-    p.row_a0 = 0; p.row_an = c->nyl; p.row_b0 = 0; p.nrows = c->nyl;
+    p.row_a0 = 0; p.row_an = c->nyl; p.row_b0 = 0; p.row_bn = 1 << 30; p.row_c0 = 0; p.nrows = c->nyl;
+    p.p2p_rows = 1 << 30;  // P2P launches: every CTA takes part unless the caller narrows it to the edge rows
     p.wrap_y = c->desc.world == 1;
     fill_collision_consts<T>(p, c->desc.collision, c->desc.tau, c->desc.ntau, c->li);
     p.force_mode = c->force_mode;
@@ -557,6 +558,15 @@ static int do_collide(lbm_ctx *c, long long step) {
 }
 
 // one fused step: buf[src] holds post-collision populations of the previous step
+// Peer-memory y-slabs: one merged launch per step, or a boundary-row launch next to an interior launch?  Measured on
+// 2 x B200 (profiles/r02/r16_*.json): 1024 x 1024 per GPU 69.3 vs 65.1 GLUPS (the merged form saves a kernel node and the
+// fork / join events: 30.3 vs 32.2 us per step), 1024 x 4096 per GPU equal, 4096 x 4096 per GPU 88.7 vs 89.9 GLUPS (there
+// the edge rows running beside the interior on a high-priority stream are worth more).  Automatic: merged up to 4 Mi nodes.
+static bool merged_launch(const lbm_ctx *c) {
+    if (c->opt_overlap == 2) return true;
+    return c->opt_overlap == 3 && (long long)c->desc.nx * c->nyl <= (1LL << 22);
+}
+
 template <typename T>
 static int do_fused(lbm_ctx *c, int src, int dst, long long step) {
     KParams<T> p = make_params<T>(c, src, dst);
@@ -572,6 +582,18 @@ static int do_fused(lbm_ctx *c, int src, int dst, long long step) {
             return 0;
         }
         run_step<T>(c, true, p, step);
+    } else if (c->p2p_on && c->opt_p2p && merged_launch(c)) {
+        // Merged launch: ONE kernel per step.  Its first CTAs (block order = launch order) take the 2H edge rows: they wait
+        // for the neighbours' previous epoch, compute, store locally and into the neighbours' ghost rows, and publish
+        // this epoch as soon as the edge rows are done; the remaining CTAs do the interior rows, which read no ghost
+        // row, and take no part in the protocol.  Saves a kernel node and the fork / join events of the two-launch form.
+        if (c->comm_pending) { CU(cudaStreamWaitEvent(c->stream, c->ev_c, 0)); c->comm_pending = false; }
+        KParams<T> pm = p;
+        pm.row_a0 = 0; pm.row_an = H; pm.row_b0 = c->nyl - H; pm.row_bn = H; pm.row_c0 = H; pm.nrows = c->nyl;
+        pm.p2p_rows = 2 * H;
+        run_step_p2p<T>(c, pm, dst, step, c->stream);
+        CU(cudaGetLastError());
+        return 0;
     } else if (c->p2p_on && c->opt_p2p) {
         // Peer-memory exchange: the boundary launch itself writes its rows into the neighbours' ghost rows and
         // hand-shakes through flags in peer memory (kernels_inst.cu), concurrently with the interior launch:

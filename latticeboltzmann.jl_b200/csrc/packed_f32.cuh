@@ -134,7 +134,11 @@ __global__ void __launch_bounds__(256, MINB) k_step_x2(const __grid_constant__ K
     // from its right neighbour (the first out-of-range lane), so no special case is needed there.
     const bool valid = x0 < p.nx;
     const int xl = valid ? x0 : 0;
-    if constexpr (P2P) p2p_wait(p);
+    bool edge_cta = false;  // see k_step: only CTAs that start inside the edge rows take part in the halo protocol
+    if constexpr (P2P) {
+        edge_cta = (int)(blockIdx.y * blockDim.y) < p.p2p_rows;
+        if (edge_cta) p2p_wait(p);
+    }
     const LatConst<float> &c = c_lat32;
     X2Consts k;
     k.cs = f2(c.css); k.half = f2(0.5f); k.sixth = f2(1.0f / 6); k.t24 = f2(1.0f / 24); k.m3 = f2(-3.0f);
@@ -217,7 +221,13 @@ __global__ void __launch_bounds__(256, MINB) k_step_x2(const __grid_constant__ K
             }
         }
     }
-    if constexpr (P2P) p2p_signal(p);
+    if constexpr (P2P) {
+        if (edge_cta) {
+            int edge_y = (p.p2p_rows + (int)blockDim.y - 1) / (int)blockDim.y;
+            if (edge_y > (int)gridDim.y) edge_y = (int)gridDim.y;
+            p2p_signal(p, (unsigned long long)gridDim.x * (unsigned long long)edge_y);
+        }
+    }
 }
 
 template <int CM, bool PULL, int MINB, bool P2P = false>

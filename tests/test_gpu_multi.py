@@ -162,6 +162,20 @@ def test_persistent_kernel_slabs_at_production_sizes(lattice, model, walls, nx, 
     _run_slabs(lattice, model, walls, 1, 1, nx=nx, ny=ny, nsteps=nsteps, persistent=1)
 
 
+@pytest.mark.parametrize("lattice,model,walls,nx,ny,nsteps,single_steps", [
+    ("D2Q9", "TRT", False, 40, 37, 9, False), ("D2Q9", "SRT", True, 40, 37, 9, False),
+    ("D2Q9", "TRT", False, 1024, 203, 60, False),   # many CTAs per row, uneven slabs, graph replays
+    ("D2Q9", "SRT", True, 1024, 512, 101, False),   # C3-like channel, odd step count
+    ("D2Q37", "TRT", True, 515, 47, 24, False),     # halo 3, odd width: the edge rows span several row groups
+    ("D2Q13", "MRT", False, 300, 64, 40, True),     # one batch per step
+    ("D2Q21", "TRT", False, 64, 13, 12, True),      # thin slabs: falls back to the whole-slab launch
+])
+def test_merged_boundary_and_interior_launch(lattice, model, walls, nx, ny, nsteps, single_steps):
+    """Option overlap = 2: ONE launch per step on a y-slab -- its first CTAs take the edge rows and the halo hand-shake, the
+    rest the interior rows.  Bit-identical (SRT / TRT) to the single-domain oracle like the two-launch form."""
+    _run_slabs(lattice, model, walls, 2, 1, nx=nx, ny=ny, nsteps=nsteps, single_steps=single_steps, persistent=0)
+
+
 @pytest.mark.parametrize("world", [3, 4, 8])
 @pytest.mark.parametrize("lattice,model,walls", [("D2Q9", "TRT", True), ("D2Q37", "TRT", False)])
 def test_more_slabs(world, lattice, model, walls):
