@@ -177,11 +177,13 @@ def test_merged_boundary_and_interior_launch(lattice, model, walls, nx, ny, nste
 
 
 @pytest.mark.parametrize("world", [3, 4, 8])
+@pytest.mark.parametrize("overlap", [1, 2])
 @pytest.mark.parametrize("lattice,model,walls", [("D2Q9", "TRT", True), ("D2Q37", "TRT", False)])
-def test_more_slabs(world, lattice, model, walls):
+def test_more_slabs(world, lattice, model, walls, overlap):
+    """Rings of 3 / 4 / 8 slabs (distinct up and down neighbours), two-launch and merged-launch forms."""
     if _gpus() < world:
         pytest.skip(f"needs {world} GPUs")
-    _run_slabs(lattice, model, walls, 1, 1, world=world, nx=136, ny=16 * world + 5, nsteps=15)
+    _run_slabs(lattice, model, walls, overlap, 1, world=world, nx=136, ny=16 * world + 5, nsteps=15)
 
 
 def test_ranks_agree_on_the_halo_path_when_one_cannot_map_its_neighbours():
