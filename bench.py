@@ -623,7 +623,9 @@ def run_b200(a):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "bytes_per_update": b_alg,
-                         "kernel_ms": kern_ms, "kernel": "k_step<%s, %s, pull>" % (type(cm).__name__, a.dtype)},
+                         "kernel_ms": kern_ms, "kernel": "k_step<%s, %s, pull>" % (type(cm).__name__, a.dtype),
+                         "note": "peak is the measured COPY bandwidth (MEASURED_PEAKS.json); a fused read+write kernel with L2 "
+                                 "prefetch can exceed it (nominal HBM3e: 7.7-8 TB/s)" if achieved > peak else None},
             "cpu_baseline": cpu,
             "parity_check": parity,
             "also": also,

@@ -192,6 +192,7 @@ struct lbm_ctx {
     // TMA-staged fused step (tma.cuh): the two population buffers as 3-D tensor maps (pitch, rows incl. ghosts, Q)
     alignas(64) CUtensorMap tmap[2];
     bool tma_ok = false;
+    int opt_prefetch = -1;  // L2-prefetch distance (rows) of the fused pull; 0 = off, -1 = automatic (prefetch_rows)
     int opt_tma = 2;      // 0 = never, 1 = wherever available, 2 = automatic (tma_auto)
     int opt_tma_cfg = 0;  // tuning: 100 * (CTA width / 128) + 10 * stages + CTAs per SM; 0 = default
     // page-locked chunk buffers for copies from / to pageable host arrays (HostPipe)
@@ -257,6 +258,8 @@ static void fill_collision_consts(P &p, int collision, const double *tau, int nt
     }
 }
 
+static int prefetch_rows(const lbm_ctx *c);
+
 template <typename T>
 static KParams<T> make_params(const lbm_ctx *c, int src, int dst) {
     KParams<T> p;
@@ -276,6 +279,7 @@ static KParams<T> make_params(const lbm_ctx *c, int src, int dst) {
     p.y0g = c->y0;
     p.nyg = c->desc.ny;
     p.row_a0 = 0; p.row_an = c->nyl; p.row_b0 = 0; p.row_bn = 1 << 30; p.row_c0 = 0; p.nrows = c->nyl;
+    p.pf_rows = prefetch_rows(c);
     p.p2p_rows = 1 << 30;  // P2P launches: every CTA takes part unless the caller narrows it to the edge rows
     p.wrap_y = c->desc.world == 1;
     fill_collision_consts<T>(p, c->desc.collision, c->desc.tau, c->desc.ntau, c->li);
@@ -492,6 +496,34 @@ static int p2p_check(lbm_ctx *c) {
         return fail(LBM_ERR_STATE, "peer-memory halo exchange timed out waiting for a neighbour (epoch/token %llu); the "
                                    "populations of this context are invalid", c->p2p_failed);
     return 0;
+}
+
+// L2-prefetch distance of the fused pull kernel (rows ahead of the row a CTA is working on; one lane per 128-byte line
+// issues prefetch.global.L2 for every population).  Measured on B200 (profiles/r02/prefetch_sweep_v2.jsonl, fraction of the
+// measured copy peak, off -> best): Float64 D2Q9 TRT 0.982 -> 1.019 (16 rows), D2Q9 MRT 0.976 -> 1.017, D2Q13 0.994 -> 1.004
+// (8), D2Q17 TRT 0.951 -> 0.964 (16), D2Q17 MRT 0.909 -> 0.939 (24), D2Q21 0.951 -> 0.962 (12), D2Q37 TRT 0.936 -> 0.943 (4),
+// D2Q37 MRT 0.855 -> 0.871 (16); distances of 64+ rows lose (the lines are evicted before use).  Float32 loses ~14 % at
+// every distance (those kernels are issue-bound: Q more instructions per node cost more than the latency they hide).
+// What matters is the distance in NODES (the sweep ran at 4096 / 2048 nodes per row): the same number of rows on a
+// 32768-wide grid is 8x further ahead in time and the lines are evicted before use (32768^2 fell from 45.3 to 33.0 GLUPS
+// with a fixed 16 rows), so the automatic distance is a node count converted to rows of this grid.
+static int prefetch_rows(const lbm_ctx *c) {
+    if (c->opt_prefetch >= 0) return c->opt_prefetch;
+    if (c->desc.dtype != LBM_F64) return 0;
+    const bool mrt = c->desc.collision == LBM_MRT;
+    const int Q = c->li.Q;
+    long long nodes;  // best distance of the sweep x nodes per row of the sweep
+    if (Q <= 9) nodes = 16 * 4096;
+    else if (Q <= 13) nodes = 8 * 4096;
+    else if (Q <= 17) nodes = (mrt ? 24 : 16) * 2048;
+    else if (Q <= 25) nodes = 12 * 2048;
+    else nodes = (mrt ? 16 : 4) * 2048;
+    const long long nx = c->desc.nx;
+    long long rows = (nodes + nx / 2) / nx;
+    if (rows < 1) rows = 1;
+    // small slabs are launch-bound and only pay the extra instructions (512^2: 0.71 -> 0.67 with prefetch)
+    if (rows * 4 > c->nyl || nx * c->nyl < (1LL << 21)) return 0;
+    return (int)rows;
 }
 
 template <typename T>
@@ -1743,6 +1775,7 @@ int lbm_set_option(lbm_ctx *c, const char *key, int64_t value) {
     else if (!strcmp(key, "overlap")) c->opt_overlap = (int)value;
     else if (!strcmp(key, "p2p")) c->opt_p2p = (int)value;
     else if (!strcmp(key, "persistent")) c->opt_persistent = (int)value;
+    else if (!strcmp(key, "prefetch")) c->opt_prefetch = (int)value;
     else if (!strcmp(key, "tma")) c->opt_tma = (int)value;
     else if (!strcmp(key, "tma_cfg")) c->opt_tma_cfg = (int)value;
     else return fail(LBM_ERR_INVALID, "unknown option '%s'", key);
@@ -1776,10 +1809,19 @@ int lbm_moments(lbm_ctx *c, double tau_visc, double *rho, double *ux, double *uy
     else c->ops->moments32(pull, make_params<float>(c, c->cur, c->cur), m, c->stream);
     c->launches += 1;
     cudaError_t e = cudaGetLastError();
-    for (int k = 0; k < 8 && e == cudaSuccess; ++k)
-        if (host[k]) e = cudaMemcpyAsync(host[k], dev[k], N * 8, cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) return fail(LBM_ERR_CUDA, "lbm_moments: %s", cudaGetErrorString(e));
+    {   // fields -> host: page-locked arrays directly, pageable ones through the chunk pipeline (several host threads)
+        HostPipe pipe(c);
+        const size_t rowbytes = (size_t)c->desc.nx * 8;
+        for (int k = 0; k < 8; ++k) {
+            if (!host[k]) continue;
+            if (is_pinned(host[k])) { CU(cudaMemcpyAsync(host[k], dev[k], N * 8, cudaMemcpyDeviceToHost, c->stream)); }
+            else { int rc2 = pipe.get((const char *)dev[k], rowbytes, (char *)host[k], rowbytes, (size_t)c->nyl); if (rc2) return rc2; }
+        }
+        int rc2 = pipe.drain();
+        if (rc2) return rc2;
+    }
+    CU(cudaStreamSynchronize(c->stream));
     return p2p_check(c);
 }
 
