@@ -1217,17 +1217,17 @@ static void launch_step_impl(int cm, bool pull, const KParams<T> &p, long long s
     if constexpr (LBM_FAST && std::is_same<T, float>::value) {
         // Float32 fast mode: packed two-nodes-per-thread kernel (variant 99 forces the scalar one)
         // (measured faster for Q <= 13; the wide lattices run out of registers with 64-bit pairs -- variant 98 forces it)
-        if (((Q <= 13 && variant != 99) || variant == 98) && (cm == LBM_SRT || cm == LBM_TRT) && p.nx % 2 == 0 && p.nx >= 2) {
-            if constexpr (P2P) {
-                if (cm == LBM_SRT) launch_step_x2<LBM_SRT, true, X2_MINB, true>(p, step, s);
-                else launch_step_x2<LBM_TRT, true, X2_MINB, true>(p, step, s);
-            } else if (cm == LBM_SRT) {
-                if (pull) launch_step_x2<LBM_SRT, true, X2_MINB>(p, step, s);
-                else launch_step_x2<LBM_SRT, false, X2_MINB>(p, step, s);
-            } else {
-                if (pull) launch_step_x2<LBM_TRT, true, X2_MINB>(p, step, s);
-                else launch_step_x2<LBM_TRT, false, X2_MINB>(p, step, s);
-            }
+        if (((Q <= 13 && variant != 99) || variant == 98) && (cm == LBM_SRT || cm == LBM_TRT || cm == LBM_MRT) && p.nx % 2 == 0 && p.nx >= 2) {
+#define LBM_X2(CM_)                                                                 \
+    {                                                                               \
+        if constexpr (P2P) launch_step_x2<CM_, true, X2_MINB, true>(p, step, s);    \
+        else if (pull) launch_step_x2<CM_, true, X2_MINB>(p, step, s);              \
+        else launch_step_x2<CM_, false, X2_MINB>(p, step, s);                       \
+    }
+            if (cm == LBM_SRT) LBM_X2(LBM_SRT)
+            else if (cm == LBM_TRT) LBM_X2(LBM_TRT)
+            else LBM_X2(LBM_MRT)
+#undef LBM_X2
             return;
         }
     }

@@ -1,5 +1,5 @@
 // Blackwell packed-FP32 variant of the fused collide+stream kernel (Float32 contexts, fast mode,
-// SRT and TRT).  Included by kernels_inst.cu inside namespace lbm::LBM_NS.
+// SRT, TRT and regularised MRT).  Included by kernels_inst.cu inside namespace lbm::LBM_NS.
 //
 // One thread owns TWO x-adjacent nodes: populations travel as 64-bit pairs (LDG.64 / STG.64 on the
 // 8-byte aligned rows) and all collision arithmetic runs on the sm_100 packed pipes (FFMA2 / FADD2 /
@@ -172,16 +172,104 @@ __global__ void __launch_bounds__(256, MINB) k_step_x2(const __grid_constant__ K
                 uy = fma2(f2(p.shift), f2(Fy0, Fy1), uy);
             }
         }
+        const unsigned n = (unsigned)y * (unsigned)p.pitch + (unsigned)xl;
+        auto emit = [&](auto I, f2 v) {
+            if (valid) *reinterpret_cast<float2 *>(p.dstp[decltype(I)::value] + n) = make_float2(v.lo(), v.hi());
+        };
+        if constexpr (CM == LBM_MRT) {
+            // regularised MRT (mrt.jl:56-118) on node pairs: the arithmetic of collide_node<LBM_MRT> (symmetric tensors
+            // reduced to their unique components, populations folded per opposite pair) in packed form
+            f2 a2[3] = {f2(0.0f), f2(0.0f), f2(0.0f)}, a3[4] = {f2(0.0f), f2(0.0f), f2(0.0f), f2(0.0f)};
+            f2 a4[5] = {f2(0.0f), f2(0.0f), f2(0.0f), f2(0.0f), f2(0.0f)};
+            const bool do2 = NH >= 2 && !p.mrt_skip[2], do3 = NH >= 3 && !p.mrt_skip[3], do4 = NH >= 4 && !p.mrt_skip[4];
+            if (do2 || do3 || do4) {
+                static_for<0, Q>([&](auto I) {
+                    constexpr int i = decltype(I)::value;
+                    constexpr int o = L::opp(i);
+                    if constexpr (i <= o) {
+                        f2 fs = g[i];
+                        if constexpr (i != o) fs = g[i] + g[o];
+                        if constexpr (NH >= 2) {
+                            if (do2) {
+#pragma unroll
+                                for (int q = 0; q < 3; ++q) a2[q] = fma2(fs, f2(c.H2[i][q]), a2[q]);
+                            }
+                        }
+                        if constexpr (NH >= 3 && i != o) {
+                            if (do3) {
+                                const f2 fa = g[i] - g[o];
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) a3[q] = fma2(fa, f2(c.H3[i][q]), a3[q]);
+                            }
+                        }
+                        if constexpr (NH >= 4) {
+                            if (do4) {
+#pragma unroll
+                                for (int q = 0; q < 5; ++q) a4[q] = fma2(fs, f2(c.H4[i][q]), a4[q]);
+                            }
+                        }
+                    }
+                });
+            }
+            const f2 xx = ux * ux, xy = ux * uy, yy = uy * uy;
+            if constexpr (NH >= 2) {
+                const f2 e[3] = {rho * xx, rho * xy, rho * yy};
+                const float m[3] = {1.0f, 2.0f, 1.0f};
+#pragma unroll
+                for (int q = 0; q < 3; ++q) a2[q] = f2(p.kn[2] * m[q]) * fma2(f2(p.c[4]), a2[q], f2(p.c[5]) * e[q]);
+            }
+            if constexpr (NH >= 3) {
+                const f2 e[4] = {rho * (xx * ux), rho * (xx * uy), rho * (xy * uy), rho * (yy * uy)};
+                const float m[4] = {1.0f, 3.0f, 3.0f, 1.0f};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) a3[q] = f2(p.kn[3] * m[q]) * fma2(f2(p.c[6]), a3[q], f2(p.c[7]) * e[q]);
+            }
+            if constexpr (NH >= 4) {
+                const f2 e[5] = {rho * (xx * xx), rho * (xx * xy), rho * (xx * yy), rho * (xy * yy), rho * (yy * yy)};
+                const float m[5] = {1.0f, 4.0f, 6.0f, 4.0f, 1.0f};
+#pragma unroll
+                for (int q = 0; q < 5; ++q) a4[q] = f2(p.kn[4] * m[q]) * fma2(f2(p.c[8]), a4[q], f2(p.c[9]) * e[q]);
+            }
+            const f2 csrho = k.cs * rho;
+            const f2 ux2 = ux + ux, ux3 = ux2 + ux, uy2 = uy + uy, uy3 = uy2 + uy;
+            static_for<0, Q>([&](auto I) {
+                constexpr int i = decltype(I)::value;
+                constexpr int o = L::opp(i);
+                if constexpr (i <= o) {
+                    const f2 w(c.w[i]);
+                    f2 even = drho;  // deviations: sum(w H_n) = 0 for n <= N
+                    if constexpr (NH >= 2) {
+                        f2 hs = a2[0] * f2(c.H2[i][0]);
+                        hs = fma2(a2[1], f2(c.H2[i][1]), hs);
+                        hs = fma2(a2[2], f2(c.H2[i][2]), hs);
+                        if constexpr (NH >= 4) {
+#pragma unroll
+                            for (int q = 0; q < 5; ++q) hs = fma2(a4[q], f2(c.H4[i][q]), hs);
+                        }
+                        even = even + hs;
+                    }
+                    if constexpr (i == o) {
+                        emit(I, w * even);
+                    } else {
+                        f2 odd = csrho * cdot2<L::cx(i), L::cy(i)>(ux, ux2, ux3, uy, uy2, uy3);
+                        if constexpr (NH >= 3) {
+                            f2 ho = a3[0] * f2(c.H3[i][0]);
+#pragma unroll
+                            for (int q = 1; q < 4; ++q) ho = fma2(a3[q], f2(c.H3[i][q]), ho);
+                            odd = odd + ho;
+                        }
+                        emit(I, w * (even + odd));
+                        emit(std::integral_constant<int, o>{}, w * (even - odd));
+                    }
+                }
+            });
+        } else {
         const f2 b = k.cs * fma2(ux, ux, uy * uy);  // css u.u
         f2 hb_e4(0.0f);  // u-only part of the even polynomial: -b/2 (order >= 2) + b^2/8 (order 4)
         if constexpr (L::EQ_ORDER >= 2) hb_e4 = f2(0.0f) - k.half * b;
         if constexpr (L::EQ_ORDER >= 4) hb_e4 = fma2(k.eighth * b, b, hb_e4);
         const f2 ax = k.cs * ux, ay = k.cs * uy;  // css u, so that a1 = c . (css u)
         const f2 ax2 = ax + ax, ax3 = ax2 + ax, ay2 = ay + ay, ay3 = ay2 + ay;
-        const unsigned n = (unsigned)y * (unsigned)p.pitch + (unsigned)xl;
-        auto emit = [&](auto I, f2 v) {
-            if (valid) *reinterpret_cast<float2 *>(p.dstp[decltype(I)::value] + n) = make_float2(v.lo(), v.hi());
-        };
         static_for<0, Q>([&](auto I) {
             constexpr int i = decltype(I)::value;
             constexpr int o = L::opp(i);
@@ -210,6 +298,7 @@ __global__ void __launch_bounds__(256, MINB) k_step_x2(const __grid_constant__ K
                 }
             }
         });
+        }  // SRT / TRT
         if (valid) {
             store_images(p, xl, y);
             store_images(p, xl + 1, y);
