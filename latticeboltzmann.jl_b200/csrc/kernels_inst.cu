@@ -647,7 +647,7 @@ __global__ void __launch_bounds__(256, MINB) k_step(const __grid_constant__ KPar
 #pragma unroll
         for (int j = 0; j < NPT; ++j)
             if (r0 + j < p.nrows) load_node<T, PULL>(p, x, launched_row(p, r0 + j), f[j]);
-        if constexpr (PULL && !P2P) {
+        if constexpr (PULL) {
             // L2 prefetch of the rows a later wave of CTAs will pull (option "prefetch" = distance in rows; 0 = off): one
             // lane per 128-byte line asks for line (y + pf_rows) of every population
             if (p.pf_rows > 0 && (threadIdx.x & (128 / sizeof(T) - 1)) == 0) {
