@@ -421,6 +421,25 @@ function b200_apply!(bcs::AbstractVector, q::Quadrature, f_new::Array{Float64, 3
 end
 
 # ------------------------------------------------------------------------------------------------------------------
+# page-locked arrays and asynchronous copies: a stream of independent jobs with several models in flight runs at the
+# device rate (job k + 1's upload and job k - 1's download overlap job k's steps; bench.py's e2e figure)
+# ------------------------------------------------------------------------------------------------------------------
+# Array{Float64, 3}(nx, ny, Q) in page-locked host memory (lbm_host_alloc); freed by its finalizer
+function pinned_array(nx::Integer, ny::Integer, nq::Integer)
+    ptr = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:lbm_host_alloc, LIB), Cint, (Ref{Ptr{Cvoid}}, Csize_t), ptr, nx * ny * nq * sizeof(Float64)))
+    f = unsafe_wrap(Array, Ptr{Float64}(ptr[]), (Int(nx), Int(ny), Int(nq)); own = false)
+    finalizer(_ -> ccall((:lbm_host_free, LIB), Cint, (Ptr{Cvoid},), ptr[]), f)
+    f
+end
+# f must be a pinned_array and stay alive (and, for uploads, unmodified) until sync!(m)
+upload_async!(m::B200Model, f::Array{Float64, 3}) = check(ccall((:lbm_upload_f_async, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), m.ctx, f))
+download_async!(m::B200Model, f::Array{Float64, 3}) = check(ccall((:lbm_download_f_async, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), m.ctx, f))
+sync!(m::B200Model) = check(ccall((:lbm_sync, LIB), Cint, (Ptr{Cvoid},), m.ctx))
+set_option!(m::B200Model, key::AbstractString, value::Integer) =
+    check(ccall((:lbm_set_option, LIB), Cint, (Ptr{Cvoid}, Cstring, Int64), m.ctx, key, value))
+
+# ------------------------------------------------------------------------------------------------------------------
 # enable!(): the package's own entry points build / use the B200 path.  Done at run time (method overwriting is not
 # allowed during precompilation): `simulate(problem, q; ...)` (lattice_boltzmann_model.jl:34-59) constructs a B200Model,
 # and -- with array_ops = true -- the array-level generic functions run on the device as well.

@@ -166,7 +166,7 @@ def _c_kind(ctype):
     t = ctype.strip()
     if "*" in t or "[" in t:
         return "ptr"
-    for k in ("int64_t", "int32_t", "double", "float"):
+    for k in ("int64_t", "int32_t", "double", "float", "size_t"):
         if k in t.split():
             return k
     if "int" in t.split():
@@ -175,7 +175,7 @@ def _c_kind(ctype):
 
 
 _JULIA_KIND = {"Int64": "int64_t", "Int32": "int32_t", "Cint": "int32_t", "Cdouble": "double", "Float64": "double",
-               "Cfloat": "float", "Cstring": "ptr"}
+               "Cfloat": "float", "Cstring": "ptr", "Csize_t": "size_t"}
 
 
 def _julia_kind(jt):
