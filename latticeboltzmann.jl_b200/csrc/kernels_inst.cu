@@ -1370,7 +1370,8 @@ static void launch_errors(bool pull, const KParams<T> &p, const ErrorArgs &e, cu
         }
     // CTAs per SM (measured on B200, 4096^2 D2Q9 f64, profiles/r02/diag_D2Q9_minb*.json): the 10 accumulators + stresses of
     // TrackHydrodynamicErrors want 80 registers (3 CTAs: 0.49 ms, 4 CTAs with spills: 0.53 ms); the lighter process! sums
-    // run best at 64 registers (4 CTAs: 0.28 ms, 3 CTAs: 0.30 ms).  LBM_ERRORS_MINB=3|4 overrides both (tuning hook).
+    // run best at 64 registers (4 CTAs: 0.28 ms, 3 CTAs: 0.30 ms); two rows in flight per thread at 128 registers (2 CTAs)
+    // measured 0.54 ms.  LBM_ERRORS_MINB=3|4 overrides both (tuning hook).
     static const int forced = [] { const char *e = getenv("LBM_ERRORS_MINB"); return e ? atoi(e) : 0; }();
 #define LBM_KE(MODE_, MINB_)                                                        \
     {                                                                               \
