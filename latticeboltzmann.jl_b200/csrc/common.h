@@ -49,6 +49,7 @@ struct KParams {
     int y0g, nyg;  // first global row of this slab, global row count
     // launched rows r -> local row: r < row_an ? row_a0 + r : (r - row_an < row_bn ? row_b0 + r - row_an : row_c0 + r - row_an - row_bn)
     int row_a0, row_an, row_b0, row_bn, row_c0, nrows;
+    int st_mode;   // tuning builds: cache operator of the population stores (0 default, 1 .cs, 2 .cg, 3 .wt)
     int pf_rows;   // > 0: L2-prefetch distance in rows for the fused pull (0 = off)
     int p2p_rows;  // P2P launches: the first p2p_rows launched rows are the slab's edge rows -- only the CTAs that start
                    // inside them wait for the neighbours' epoch and publish this one (nrows: every CTA, as in a launch of

@@ -667,8 +667,19 @@ __global__ void __launch_bounds__(256, MINB) k_step(const __grid_constant__ KPar
                 T Fx, Fy;
                 const bool forced = load_force(p, x, y, step, Fx, Fy);
                 const unsigned n = (unsigned)y * (unsigned)p.pitch + (unsigned)x;
+#ifdef LBM_TUNE
+                // store-policy experiment (option "store"): 1 = st.cs (evict first), 2 = st.cg, 3 = st.wt
+                collide_node<CM, T>(p, f[j], forced, Fx, Fy, [&](auto I, T v) {
+                    T *q = p.dstp[decltype(I)::value] + n;
+                    if (p.st_mode == 1) __stcs(q, v);
+                    else if (p.st_mode == 2) __stcg(q, v);
+                    else if (p.st_mode == 3) __stwt(q, v);
+                    else *q = v;
+                });
+#else
                 collide_node<CM, T>(p, f[j], forced, Fx, Fy,
                                     [&](auto I, T v) { p.dstp[decltype(I)::value][n] = v; });
+#endif
                 store_images(p, x, y);
                 if constexpr (P2P) {
                     if (y < H || y >= p.nyl - H) p2p_store(p, x, y);

@@ -192,6 +192,7 @@ struct lbm_ctx {
     // TMA-staged fused step (tma.cuh): the two population buffers as 3-D tensor maps (pitch, rows incl. ghosts, Q)
     alignas(64) CUtensorMap tmap[2];
     bool tma_ok = false;
+    int opt_store = 0;      // tuning builds: cache operator of the population stores
     int opt_prefetch = -1;  // L2-prefetch distance (rows) of the fused pull; 0 = off, -1 = automatic (prefetch_rows)
     int opt_tma = 2;      // 0 = never, 1 = wherever available, 2 = automatic (tma_auto)
     int opt_tma_cfg = 0;  // tuning: 100 * (CTA width / 128) + 10 * stages + CTAs per SM; 0 = default
@@ -280,6 +281,7 @@ static KParams<T> make_params(const lbm_ctx *c, int src, int dst) {
     p.nyg = c->desc.ny;
     p.row_a0 = 0; p.row_an = c->nyl; p.row_b0 = 0; p.row_bn = 1 << 30; p.row_c0 = 0; p.nrows = c->nyl;
     p.pf_rows = prefetch_rows(c);
+    p.st_mode = c->opt_store;
     p.p2p_rows = 1 << 30;  // P2P launches: every CTA takes part unless the caller narrows it to the edge rows
     p.wrap_y = c->desc.world == 1;
     fill_collision_consts<T>(p, c->desc.collision, c->desc.tau, c->desc.ntau, c->li);
@@ -1776,6 +1778,7 @@ int lbm_set_option(lbm_ctx *c, const char *key, int64_t value) {
     else if (!strcmp(key, "p2p")) c->opt_p2p = (int)value;
     else if (!strcmp(key, "persistent")) c->opt_persistent = (int)value;
     else if (!strcmp(key, "prefetch")) c->opt_prefetch = (int)value;
+    else if (!strcmp(key, "store")) c->opt_store = (int)value;
     else if (!strcmp(key, "tma")) c->opt_tma = (int)value;
     else if (!strcmp(key, "tma_cfg")) c->opt_tma_cfg = (int)value;
     else return fail(LBM_ERR_INVALID, "unknown option '%s'", key);

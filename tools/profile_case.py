@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--prefetch", type=int, default=-1, help="L2-prefetch distance in rows (0 = off, -1 = automatic)")
+    ap.add_argument("--store", type=int, default=0, help="tuning builds: 1 st.cs, 2 st.cg, 3 st.wt for the population stores")
     ap.add_argument("--tma", type=int, default=2, help="TMA-staged fused kernel: 0 off, 1 on, 2 automatic")
     ap.add_argument("--tma-cfg", type=int, default=0, help="100 * (CTA width / 128) + 10 * stages + CTAs per SM; 0 = default")
     ap.add_argument("--check", action="store_true", help="compare the populations after the run with a run of the register kernel")
@@ -65,13 +66,14 @@ def main():
         c.set_option("variant", a.variant)
         c.set_option("tma", a.tma)
         c.set_option("prefetch", a.prefetch)
+        c.set_option("store", a.store)
         c.set_option("tma_cfg", a.tma_cfg)
         c.set_option("persistent", a.persistent)
         c.set_option("graph", a.graph)
         c.upload_f(f0)
         c.step(0, 4)
         c.sync()
-        out = dict(lattice=a.lattice, model=a.model, dtype=a.dtype, arith=a.arith, variant=a.variant, tma=a.tma, tma_cfg=a.tma_cfg, prefetch=a.prefetch, n=n, ny=ny,
+        out = dict(lattice=a.lattice, model=a.model, dtype=a.dtype, arith=a.arith, variant=a.variant, tma=a.tma, tma_cfg=a.tma_cfg, prefetch=a.prefetch, store=a.store, n=n, ny=ny,
                    persistent=a.persistent, graph=a.graph)
         if a.diag:
             import time
