@@ -1005,6 +1005,30 @@ def test_tma_staged_kernel_equals_the_register_kernel(oracle, name, model, bck, 
             assert np.array_equal(outs[0], want)
 
 
+def test_l2_prefetch_does_not_change_results(oracle):
+    """Option prefetch (L2 prefetch distance of the fused pull, automatic for Float64 on grids of 2 Mi nodes and more): a
+    hint only -- populations are bit-identical with it forced on (several distances, one beyond the grid) and off."""
+    O = oracle
+    qo = O.L.D2Q13()
+    nx, ny, nsteps = 300, 70, 11
+    f0 = random_populations(qo, nx, ny, seed=8)
+    cm, code, taus = _models(O, qo, (1e-6, 0.0))["TRT"]
+    ob, hb = _bcs_pair(O, "poiseuille", nx, ny)
+    outs = []
+    for pf in (0, 1, 16, 200):
+        with _ctx("D2Q13", code, taus, hb, nx, ny, _abi.ARITH_EXACT, _abi.F64) as c:
+            c.set_option("prefetch", pf)
+            c.set_force_uniform(1e-6, 0.0)
+            c.upload_f(to_host_layout(f0))
+            c.step(0, nsteps)
+            outs.append(to_oracle_layout(c.download_f()))
+    want = f0
+    for _ in range(nsteps):
+        want, _ = O.step(cm, qo, ob, want)
+    for o in outs:
+        assert np.array_equal(o, want)
+
+
 def test_timer_and_options():
     with _abi.Context(64, 64, "D2Q9", _abi.SRT, [0.9]) as c:
         c.upload_f(np.asfortranarray(np.ones((64, 64, 9)) * lbm.D2Q9().weights))
