@@ -648,15 +648,20 @@ __global__ void __launch_bounds__(256, MINB) k_step(const __grid_constant__ KPar
         for (int j = 0; j < NPT; ++j)
             if (r0 + j < p.nrows) load_node<T, PULL>(p, x, launched_row(p, r0 + j), f[j]);
         if constexpr (PULL) {
-            // L2 prefetch of the rows a later wave of CTAs will pull (option "prefetch" = distance in rows; 0 = off): one
-            // lane per 128-byte line asks for line (y + pf_rows) of every population
-            if (p.pf_rows > 0 && (threadIdx.x & (128 / sizeof(T) - 1)) == 0) {
+            // L2 prefetch of the row a later wave of CTAs will pull (option "prefetch" = distance in rows; 0 = off).  ONE warp
+            // per CTA asks for the CTA's 128-byte lines of every population pf_rows rows ahead: Q * (CTA width * sizeof(T) /
+            // 128) prefetches spread over 32 lanes -- a handful of instructions for one warp instead of Q for every warp
+            // (profiles/r02/ncu_summary.md: the per-warp form added 14 % instructions; Float32 lost more than it gained).
+            if (p.pf_rows > 0 && blockDim.y == 1 && threadIdx.x < 32) {
                 const int yp = launched_row(p, r0) + p.pf_rows;
                 if (yp < p.nyl) {
-                    const unsigned np = (unsigned)yp * (unsigned)p.pitch + (unsigned)x;
-                    static_for<0, Q>([&](auto I) {
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.srcp[decltype(I)::value] + np));
-                    });
+                    constexpr int EPL = 128 / (int)sizeof(T);                  // elements per line
+                    const int lines = ((int)blockDim.x + EPL - 1) / EPL;       // lines of one population under this CTA
+                    const unsigned base = (unsigned)yp * (unsigned)p.pitch + blockIdx.x * blockDim.x;
+                    for (int k = threadIdx.x; k < Q * lines; k += 32) {
+                        const int i = k / lines, l = k - i * lines;
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.srcp[i] + base + (unsigned)(l * EPL)));
+                    }
                 }
             }
         }
