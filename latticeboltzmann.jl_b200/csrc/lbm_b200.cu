@@ -1099,13 +1099,21 @@ static void par_memcpy(void *dst, const void *src, size_t bytes) {
     const size_t slice = ((bytes + nthreads - 1) / nthreads + 63) & ~(size_t)63;
     std::thread th[8];
     int started = 0;
+    size_t covered = slice < bytes ? slice : bytes;  // [0, covered) is this thread's share; helpers take what follows
     for (int t = 1; t < nthreads; ++t) {
         const size_t off = (size_t)t * slice;
         if (off >= bytes) break;
         const size_t n = bytes - off < slice ? bytes - off : slice;
-        th[started++] = std::thread([=] { memcpy((char *)dst + off, (const char *)src + off, n); });
+        try {
+            th[started] = std::thread([=] { memcpy((char *)dst + off, (const char *)src + off, n); });
+        } catch (...) {  // no more threads to be had (never let an exception cross the C ABI): copy the rest here
+            break;
+        }
+        ++started;
+        covered = off + n;
     }
     memcpy(dst, src, slice < bytes ? slice : bytes);
+    if (covered < bytes) memcpy((char *)dst + covered, (const char *)src + covered, bytes - covered);
     for (int t = 0; t < started; ++t) th[t].join();
 }
 
