@@ -1343,7 +1343,7 @@ static inline dim3 reduce_grid(int nx, int nyl, const dim3 &block, int cap, int 
     const long long gx = (nx + block.x - 1) / block.x, gy_nat = (nyl + block.y - 1) / block.y;
     long long rpt = (gx * gy_nat) / (148 * 8);          // rows per thread that still leave ~8 CTAs per SM
     rpt = rpt < 1 ? 1 : (rpt > 16 ? 16 : rpt);
-    while (gx * ((gy_nat + rpt - 1) / rpt) > cap) ++rpt;
+    while (gx * ((gy_nat + rpt - 1) / rpt) > cap && rpt < gy_nat) ++rpt;  // (gx <= cap is checked by the callers)
     *rows_per_cta = (int)(rpt * block.y);
     return dim3((unsigned)gx, (unsigned)((gy_nat + rpt - 1) / rpt), 1);
 }

@@ -1881,6 +1881,7 @@ static int reduce_errors_mode(lbm_ctx *c, int mode, double tau_visc, double u_ma
     const int nx = c->desc.nx, nyl = c->nyl, W = nx + nyl;
     const size_t tabn = (size_t)16 * W;
     const int nblocks = 8192;
+    if (((long long)nx + 31) / 32 > nblocks) return fail(LBM_ERR_UNSUPPORTED, "reductions support at most %d columns", 32 * nblocks);
     const size_t need = tabn + (size_t)nblocks * 16 + 16;
     if (c->err_doubles < need) {
         if (c->err_dev) { CU(cudaStreamSynchronize(c->stream)); cudaFree(c->err_dev); c->err_dev = nullptr; c->err_doubles = 0; }
@@ -1946,6 +1947,8 @@ int lbm_reduce(lbm_ctx *c, int32_t kind, double *out, int32_t n) {
     CU(cudaSetDevice(c->desc.device));
     int rc = wait_comm(c);
     if (rc) return rc;
+    // one partial per CTA, CTAs at most 256 columns wide: rows wider than 256 x red_blocks columns do not fit the buffer
+    if (((long long)c->desc.nx + 31) / 32 > c->red_blocks) return fail(LBM_ERR_UNSUPPORTED, "reductions support at most %d columns", 32 * c->red_blocks);
     const size_t N = (size_t)c->nyl * c->desc.nx;
     if (kind == LBM_REDUCE_VELOCITY_CHANGE && !c->u_old) {
         CU(cudaMalloc(&c->u_old, 2 * N * 8));
